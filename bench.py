@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its config, one JSON line on stdout (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1 workload (BASELINE.json configs[1]): Llama-2-7B-shape, w4 g128 r128, batch 1 decode: one "step" is
+one token through the 224 packed QuantLinear GEMVs of the 32 decoder blocks (3.701 GB of algorithmic bytes,
+far larger than the 126 MB L2, so every step streams its weights from HBM).
+N > 1 workload (configs[4]): Llama-2-70B shapes, every linear column-sharded over the N ranks, NCCL
+all-gather of each projection group's output over NVLink; strong scaling (total work fixed).
+
+`--impl reference`: the reference has no CPU implementation of this path (every forward calls its CUDA
+extension), so this arm times the oracle's restatement of the reference arithmetic ("torch dequant+matmul on
+CPU", BASELINE.json configs[0]) with all host threads on a bounded sample: one decoder block per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "QuantLinear GEMV HBM GB/s & decode tok/s, GEMM TFLOP/s (Llama-2-7B w4g128r128)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=None, help="7b | 13b | 70b (default: 7b at N=1, 70b at N>1)")
+    ap.add_argument("--layers", type=int, default=None, help="debug: fewer decoder blocks (INVALID as a bench number)")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fused", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", action="store_true", help="also time the prefill GEMM (M=2048) and report TFLOP/s")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()   # exact PID we started
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "gemv_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_block_baseline(model="7b", reps=1, warm=0, threads=None):
+    """Oracle port of the reference arithmetic on the host: one decoder block, batch 1 (bounded sample)."""
+    import numpy as np
+    import torch
+    import oracle
+    from qeft_b200.synth import decoder_linears
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    layers = []
+    for i, (name, N, K) in enumerate(decoder_linears(model)):
+        layers.append(oracle.synth_layer(N, K, seed=1000 + i))
+    rng = np.random.default_rng(0)
+    xs = [rng.standard_normal((1, L["K"])).astype(np.float16) for L in layers]
+    nbytes = sum(oracle.gemv_algorithmic_bytes(L["N"], L["K"]) for L in layers)
+    times = []
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        for L, x in zip(layers, xs):
+            oracle.cpu_dequant_matmul(x, L)
+        dt = time.perf_counter() - t0
+        if it >= warm:
+            times.append(dt)
+    return nbytes, times, threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = args.model or "7b"
+    from qeft_b200.synth import LLAMA_SHAPES
+    nl = LLAMA_SHAPES[model][2]
+    nbytes, times, threads = cpu_block_baseline(model, reps=max(1, args.steps), warm=args.warmup)
+    t = statistics.median(times)
+    gbs = nbytes / t / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"llama2-{model} decode b1, packed QuantLinear stack w4 g128 r128",
+                   "sample": f"1 of {nl} decoder blocks per step (7 dequant+matmul calls); tok/s extrapolated x{nl}"},
+        "decode_tok_s": 1.0 / (t * nl),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
+                         "sample": f"one llama2-{model} decoder block (7 linears, {nbytes} algorithmic bytes) per step, "
+                                   f"median of {len(times)}"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from qeft_b200 import qeft_cuda
+    from qeft_b200.decode import PackedDecoderStack
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; qeft_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model = args.model or ("7b" if world == 1 else "70b")
+    stack = PackedDecoderStack(model, layers=args.layers, fused=not args.no_fused, pdl=not args.no_pdl,
+                               shard=(rank, world), batch=args.batch, device=f"cuda:{local}")
+    if world > 1:
+        stack.enable_allgather(dist.group.WORLD)
+    if not args.no_graph:
+        stack.capture()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        stack.step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = qeft_cuda.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        stack.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = qeft_cuda.launch_count() - l0
+    if stack.graph is not None:
+        launches = stack.launches_per_step() * args.steps      # graph replays do not pass through the C ABI
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host activations in, result back on the host, every step ------------------
+    xh = torch.randn(stack.x_h.shape).half().pin_memory()
+    xf = torch.randn(stack.x_f.shape).half().pin_memory()
+    yh = torch.empty(stack.out[-1]["down"].shape, dtype=torch.float16).pin_memory()
+    for _ in range(3):
+        stack.step_from_host(xh, xf, yh)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        stack.step_from_host(xh, xf, yh)
+        torch.cuda.current_stream().synchronize()       # the caller reads y before the next token
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    nbytes = stack.algorithmic_bytes_per_step()
+    tot = torch.tensor([nbytes], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    nbytes_all = tot.item()
+
+    extra = {}
+    if args.gemm and rank == 0:
+        extra["gemm"] = bench_gemm(model)
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        gbs = nbytes_all / (ms_step * 1e-3) / 1e9
+        gbs_e2e = nbytes_all / (ms_e2e / args.steps * 1e-3) / 1e9
+        hbm_peak, _, peak_src = measured_peaks()
+        per_gpu = gbs / world
+        line = {
+            "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {
+                "workload": (f"llama2-{model} decode b{args.batch}: {stack.nlayers} decoder blocks x 7 packed QuantLinear "
+                             f"(w4 g128 r128) = {stack.launches_per_step()} GEMV launches/token"
+                             + (f", column-sharded over {world} ranks + NCCL all-gather" if world > 1 else "")),
+                "algorithmic_bytes_per_step": int(nbytes_all), "l2_policy": "inputs larger than L2 (3.7 GB of weights streamed per step)",
+                "cuda_graph": stack.graph is not None, "fused_qkv_gateup": stack.fused, "pdl": stack.pdl,
+                "layers": stack.nlayers,
+            },
+            "decode_tok_s": args.batch * 1e3 / ms_step,
+            "clocks": clocks,
+            "e2e": {"value": gbs_e2e, "unit": "GB/s", "tok_s": args.batch * 1e3 / (ms_e2e / args.steps),
+                    "h2d_bytes_per_step": int(xh.numel() * 2 + xf.numel() * 2), "d2h_bytes_per_step": int(yh.numel() * 2)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
+                         "frac_of_nominal_8TBs": per_gpu / 8000.0, "peak_source": peak_src, "kernel": "gemv_w4_kernel",
+                         "traffic": ncu_traffic()},
+        }
+        if args.layers is not None:
+            line["config"]["INVALID"] = "reduced layer count (debug run)"
+        if world == 1 and not args.no_cpu_baseline:
+            nb, times, threads = cpu_block_baseline(model if model != "70b" else "7b", reps=2, warm=1)
+            tmed = statistics.median(times)
+            line["cpu_baseline"] = {"value": nb / tmed / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+                                    "sample": f"one llama2-{model} decoder block (7 dequant+matmul calls, {nb} algorithmic bytes), "
+                                              f"median of {len(times)} after 1 warm-up; {tmed:.3f} s per block",
+                                    "tok_s_extrapolated": 1.0 / (tmed * stack.nlayers)}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_gemm(model):
+    return None
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+/*
+ * qeft_b200.h -- C ABI of the B200-native packed QuantLinear kernels.
+ *
+ * This is the drop-in boundary for the reference's `qeft_cuda` extension
+ * (qeft/kernel/qeft_cuda.cpp:10-27 in xvyaward/qeft).  Every entry point takes raw
+ * DEVICE pointers, plain ints and a CUDA stream handle, never allocates, never
+ * synchronises, and returns an int status:
+ *      0   success
+ *     <0   invalid argument (QEFT_E_*), nothing was launched
+ *     >0   a cudaError_t from the launch
+ * There is no CPU fallback: without a CUDA device every compute entry returns
+ * a cudaError_t.
+ *
+ * Packed layout (bit-exact with qeft/qlinear.py:70-121,180-215 of the reference):
+ *   qweight       int16 [N/4, K]   4 rows x 64 columns per 128-byte tile, AWQ-v2 nibble order
+ *   scales        fp16  [K/G, N]
+ *   scaled_zeros  fp16  [K/G, N]   = -(zero * scale);  w = fma(q, scale, scaled_zero)
+ *   oweight       fp16  [N, r]     dense outlier ("weak") columns = input columns K-r .. K-1
+ *   oweight_interleaved fp16 [N/2, 2r]  row-pair interleaved copy used by the reference GEMV
+ *   bias          fp16  [N] or NULL
+ * The last r int4 columns of qweight are dead (they carry the zero point) and are
+ * never read by these kernels.
+ */
+#ifndef QEFT_B200_H_
+#define QEFT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QEFT_B200_ABI_VERSION 1
+
+#if defined(_WIN32)
+#define QEFT_API
+#else
+#define QEFT_API __attribute__((visibility("default")))
+#endif
+
+/* status codes (negative = argument errors) */
+#define QEFT_OK 0
+#define QEFT_E_NULL (-1)     /* a required pointer is NULL */
+#define QEFT_E_SHAPE (-2)    /* N, K, r, G or m violate the layout's divisibility rules */
+#define QEFT_E_BATCH (-3)    /* GEMV batch outside 1..8 (reference: "Unsupported batch size for gemv kernel.") */
+#define QEFT_E_DTYPE (-4)    /* unknown dtype / layout enum */
+#define QEFT_E_ALIGN (-5)    /* pointer not 16-byte aligned */
+#define QEFT_E_UNSUPPORTED (-6)
+
+/* activation / output element type of the GEMM-class entries */
+#define QEFT_DT_F16 0
+#define QEFT_DT_BF16 1
+
+/* layout of the outlier weights handed to the GEMV */
+#define QEFT_OW_NONE 0         /* r == 0 (reference gemv_4bit) */
+#define QEFT_OW_PLAIN 1        /* oweight [N, r] */
+#define QEFT_OW_INTERLEAVED 2  /* oweight_interleaved [N/2, 2r] (reference gemv_4bit_qeft) */
+
+/* launch flags */
+#define QEFT_F_PDL 1u          /* launch with programmatic dependent launch: weight prefetch of this
+                                  kernel overlaps the tail of the previous kernel in the stream */
+
+typedef void* qeft_stream_t;   /* cudaStream_t */
+
+QEFT_API int qeft_abi_version(void);
+/* static string: build arch, compiler */
+QEFT_API const char* qeft_build_info(void);
+/* number of kernels this library has launched since load (all entry points); bench.py's gpu_launches */
+QEFT_API uint64_t qeft_launch_count(void);
+QEFT_API const char* qeft_status_string(int status);
+
+/*
+ * Decode GEMV:  y[m, N] = x[m, K] . Wdense^T (+ bias),  m in 1..8.
+ * Replaces  gemv_4bit       (qeft/kernel/quantization_new/gemv/gemv_cuda.cu:358-437)   with ow_layout = NONE
+ *      and  gemv_4bit_qeft  (qeft/kernel/quantization_new/gemv/gemv_cuda_qeft.cu:392-513) with INTERLEAVED.
+ * The outlier columns REPLACE the int4 columns (gemv_cuda_qeft.cu:168-176).
+ * x_gather (int32 [K] or NULL): when given, x[:, x_gather[k]] is read in place of x[:, k]; this fuses
+ * the o_proj `index_select(x, -1, reorder_ids)` of qeft/qlinear.py:273-275.
+ * Requires N % 8 == 0, K % 64 == 0, G % 128 == 0 (or G == K), K % G == 0, r % 32 == 0, r < K.
+ */
+QEFT_API int qeft_gemv_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
+                 const void* oweight, int ow_layout, const void* bias, const int32_t* x_gather,
+                 void* y, int m, int N, int K, int r, int G, unsigned flags, qeft_stream_t stream);
+
+/*
+ * Several GEMVs that share one x in ONE launch (q/k/v, gate/up): part p writes y[p][m, N[p]].
+ * No reference counterpart (the reference launches one kernel per projection, qlinear.py:253-263).
+ */
+typedef struct {
+  const void* qweight;
+  const void* scales;
+  const void* scaled_zeros;
+  const void* oweight;
+  const void* bias;
+  void* y;
+  int N;
+} qeft_gemv_part_t;
+
+#define QEFT_GEMV_MAX_PARTS 4
+QEFT_API int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,
+                       const int32_t* x_gather, int m, int K, int r, int G, unsigned flags,
+                       qeft_stream_t stream);
+
+/*
+ * Prefill / fine-tune GEMM:  y[M, N] = x[M, K] . Wdense^T (+ bias)  on tcgen05 tensor cores.
+ * Replaces  gemm_4bit (qeft/kernel/quantization_new/gemm/gemm_cuda.cu:929-1033)  PLUS the separate
+ * `y += F.linear(x[..., -r:], oweight)` and `y + bias` of qeft/qlinear.py:264-268 in one kernel.
+ * oweight is the PLAIN [N, r] tensor (may be NULL when r == 0).  GEMV semantics for the outlier
+ * columns (the dead int4 columns are skipped).  Requires N % 128 == 0, K % 64 == 0, r % 64 == 0, G == 128.
+ */
+QEFT_API int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
+                 const void* oweight, const void* bias, void* y, int M, int N, int K, int r, int G,
+                 int dtype, unsigned flags, qeft_stream_t stream);
+
+/*
+ * Backward wrt the input:  dx[M, K] = dy[M, N] . Wdense   (same packed bytes, contraction over N).
+ * The math BASELINE.json defines for QuantMatMulQEFT.backward (the reference's qlinear.py:28-44 is
+ * not usable).
+ */
+QEFT_API int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* scales, const void* scaled_zeros,
+                    const void* oweight, void* dx, int M, int N, int K, int r, int G,
+                    int dtype, unsigned flags, qeft_stream_t stream);
+
+/*
+ * Gradient of the trainable outlier columns:  dow[N, r] (fp32) (+)= dy[M, N]^T . x[M, K-r:K].
+ * accumulate != 0 adds into dow (gradient accumulation into the fp32 master grad).
+ */
+QEFT_API int qeft_dow(const void* dy, const void* x, float* dow, int M, int N, int K, int r,
+             int dtype, int accumulate, unsigned flags, qeft_stream_t stream);
+
+/*
+ * Device packers (bit-exact with qeft/qlinear.py:70-121).
+ *   qeft_pack_w4     : intweight int32 [N, K] (values 0..15; not clamped, like the reference) -> qweight int16 [N/4, K]
+ *   qeft_unpack_w4   : the inverse, int32 [N, K]
+ *   qeft_dequant_w4  : dense fp16 [N, K] = fma(q, s, sz); when oweight != NULL the last r columns are oweight
+ *   qeft_interleave_oweight : oweight fp16 [N, r] -> oweight_interleaved [N/2, 2r] (pack_oweight); used to
+ *                      refresh the GEMV copy after a fine-tuning step changed oweight
+ */
+QEFT_API int qeft_pack_w4(const int32_t* intweight, void* qweight, int N, int K, qeft_stream_t stream);
+QEFT_API int qeft_unpack_w4(const void* qweight, int32_t* intweight, int N, int K, qeft_stream_t stream);
+QEFT_API int qeft_dequant_w4(const void* qweight, const void* scales, const void* scaled_zeros, const void* oweight,
+                    void* w_dense, int N, int K, int r, int G, int dtype, qeft_stream_t stream);
+QEFT_API int qeft_interleave_oweight(const void* oweight, void* oweight_interleaved, int N, int r, int src_fp32,
+                            qeft_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QEFT_B200_H_ */

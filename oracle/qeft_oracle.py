@@ -51,8 +51,11 @@ def pack_intweight(q):
     tiles = q.reshape(N // 4, 4, K // 64, 64).transpose(0, 2, 1, 3).astype(np.int64)  # [b, T, j, kk]
     out = np.zeros((N // 4, K // 64, 64), dtype=np.int64)
     for jj in range(4):
-        # no clamp, like the reference: an out-of-range value spills into its neighbours
-        np.bitwise_or.at(out, (slice(None), slice(None), e[jj]), tiles[:, :, jj, :] << (4 * i[jj]))
+        for ii in range(4):
+            # no clamp, like the reference: an out-of-range value spills into its neighbours.
+            # For a fixed (row, nibble slot) the 16 target int16 numbers are distinct.
+            sel = np.nonzero(i[jj] == ii)[0]
+            out[:, :, e[jj][sel]] |= tiles[:, :, jj, sel] << (4 * ii)
     return out.reshape(N // 4, K).astype(np.uint16).view(np.int16)
 
 
@@ -249,6 +252,19 @@ def synth_layer(N, K, r=128, G=128, seed=0, bias=False, o_proj=False):
     return layer
 
 
+def _unpack_torch(qweight_t):
+    """Same map as :func:`unpack_intweight`, as torch reshapes/permutes (multi-threaded, for the timed baseline)."""
+    import torch
+
+    Nq, K = qweight_t.shape
+    v = (qweight_t.to(torch.int32) & 0xFFFF).view(Nq, K // 64, 64, 1)
+    nib = (v >> torch.tensor([0, 4, 8, 12], dtype=torch.int32).view(1, 1, 1, 4)) & 0xF      # [b, T, e, i]
+    # linear nibble index 4e+i = 64 j + 32 half + 8 g + 4 odd + q8 ;  column = 32 half + 8 q8 + 2 g + odd
+    nib = nib.reshape(Nq, K // 64, 4, 2, 4, 2, 4)                                           # [b, T, j, half, g, odd, q8]
+    nib = nib.permute(0, 2, 1, 3, 6, 4, 5)                                                  # [b, j, T, half, q8, g, odd]
+    return nib.reshape(Nq * 4, K)
+
+
 def cpu_dequant_matmul(x, layer, threads=None, cached_weight=None):
     """The "reference torch dequant+matmul on CPU" of BASELINE.json config 1, in torch.
 
@@ -263,11 +279,15 @@ def cpu_dequant_matmul(x, layer, threads=None, cached_weight=None):
     r = layer["r"]
     K = layer["K"]
     if cached_weight is None:
-        q = torch.as_tensor(unpack_intweight(layer["qweight"]))                    # int32 [N, K]
+        q = _unpack_torch(torch.as_tensor(layer["qweight"]))                        # int32 [N, K]
         G = layer["G"]
-        s = torch.as_tensor(layer["scales"]).t().repeat_interleave(G, dim=1)        # fp16 [N, K]
-        z = torch.as_tensor(layer["scaled_zeros"]).t().repeat_interleave(G, dim=1)
-        W = torch.addcmul(z.double(), q.double(), s.double()).half().float()       # single rounding
+        N = q.shape[0]
+        s = torch.as_tensor(layer["scales"]).t().float()                            # [N, K/G]
+        z = torch.as_tensor(layer["scaled_zeros"]).t().float()
+        # q*s is exact in fp32 (4-bit x 11-bit); the sum is rounded once to fp32 and again to fp16.  Double
+        # rounding can differ from the single-rounding fma by one fp16 ulp in rare ties; this function is the
+        # TIMED baseline, the checker is `forward` (float64, single rounding).
+        W = (q.view(N, K // G, G).float() * s.unsqueeze(-1) + z.unsqueeze(-1)).half().float().view(N, K)
     else:
         W = cached_weight
     xm = xt.reshape(-1, K)

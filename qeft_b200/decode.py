@@ -1,0 +1,155 @@
+"""One decode token through the packed linears of a Llama-shaped stack, as a replayable CUDA graph.
+
+This is the data-parallel hot path BASELINE.json's metric is quoted on: per decoder block the seven
+``QuantLinear`` GEMVs (reference call stack: qeft/main.py:356-366 -> HF LlamaDecoderLayer ->
+``QuantLinear.forward_outlier`` -> ``qeft_cuda.gemv_4bit_qeft``).  B200-first differences:
+
+* q/k/v and gate/up share their input, so each group is ONE launch (4 launches per block, not 7+);
+* every launch uses programmatic dependent launch, so the weight stream of launch i+1 starts
+  while launch i drains;
+* the whole token (4 x layers launches) is captured once in a CUDA graph and replayed.
+
+Attention, norms and the activation function are not part of this path (out of scope); the
+stack feeds each group from fixed activation buffers, so a step's cost is exactly the packed-linear work.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import _lib, qeft_cuda
+from .reorder import sparse_to_dense_ids
+from .synth import LLAMA_SHAPES, synth_tensors
+
+
+class PackedDecoderStack:
+    def __init__(self, model="7b", layers=None, r=128, G=128, device="cuda", seed=0, fused=True, pdl=True,
+                 shard=(0, 1), batch=1):
+        h, f, nl, kv = LLAMA_SHAPES[model]
+        self.model, self.r, self.G, self.device = model, r, G, torch.device(device)
+        self.h, self.f, self.kv = h, f, kv
+        self.nlayers = nl if layers is None else layers
+        self.fused, self.pdl, self.batch = fused, pdl, batch
+        rank, world = shard
+        self.rank, self.world = rank, world
+
+        def sl(n):   # column (output-feature) shard owned by this rank
+            assert n % (world * 16) == 0
+            return n // world
+
+        self.nq, self.nkv, self.nf, self.no = sl(h), sl(kv), sl(f), sl(h)
+        self.blocks: List[dict] = []
+        for li in range(self.nlayers):
+            blk = {}
+            for pi, (name, N, K) in enumerate((("q", self.nq, h), ("k", self.nkv, h), ("v", self.nkv, h),
+                                               ("o", self.no, h), ("gate", self.nf, h), ("up", self.nf, h),
+                                               ("down", self.no, f))):
+                blk[name] = synth_tensors(N, K, r, G, seed=seed * 100003 + li * 16 + pi + rank * 7919,
+                                          device=self.device, o_proj=(name == "o"))
+                blk[name]["N"] = N
+            if r > 0:   # o_proj gathers its outlier channels to the back (qlinear.py:273-275): fused into the GEMV
+                blk["o"]["reorder_ids32"] = sparse_to_dense_ids(blk["o"]["outlieridx"], h).to(torch.int32)
+            self.blocks.append(blk)
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed + 17)
+        m = batch
+        self.x_h = torch.randn((m, h), device=self.device, generator=g).half()     # hidden-size input (q/k/v/o/gate/up)
+        self.x_f = torch.randn((m, f), device=self.device, generator=g).half()     # ffn-size input (down)
+        # outputs: one contiguous buffer per launch group so that a sharded run needs ONE all-gather per launch
+        self.groups = (("q", "k", "v"), ("o",), ("gate", "up"), ("down",))
+        self.out, self.grp_local, self.grp_full = [], [], []
+        for blk in self.blocks:
+            o, gl = {}, []
+            for names in self.groups:
+                width = sum(blk[n]["N"] for n in names)
+                buf = torch.empty((m, width), dtype=torch.float16, device=self.device)
+                gl.append(buf)
+                off = 0
+                for n in names:
+                    # batch 1: a column slice of the group buffer is itself a contiguous [1, N] output
+                    o[n] = buf[:, off:off + blk[n]["N"]] if m == 1 else torch.empty((m, blk[n]["N"]), dtype=torch.float16,
+                                                                                     device=self.device)
+                    off += blk[n]["N"]
+            self.out.append(o)
+            self.grp_local.append(gl)
+        self.pg = None
+        self.graph = None
+
+    def enable_allgather(self, process_group):
+        """Column-sharded execution: after each launch group, all-gather the ranks' output slices (NCCL over
+        NVLink).  The gathered buffer is [world, group_width]: rank-major, then q|k|v (or gate|up) inside."""
+        assert self.batch == 1, "the sharded stack is exercised at batch 1"
+        self.pg = process_group
+        self.grp_full = [[torch.empty((self.world, b.shape[1]), dtype=torch.float16, device=self.device) for b in gl]
+                         for gl in self.grp_local]
+
+    def _gather(self, li, gi):
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.grp_full[li][gi].view(-1), self.grp_local[li][gi].view(-1), group=self.pg)
+
+    # ---- accounting -----------------------------------------------------------------------------
+    def algorithmic_bytes_per_step(self) -> int:
+        m, r, G = self.batch, self.r, self.G
+        tot = 0
+        for blk in self.blocks:
+            for n, t in blk.items():
+                N, K = t["N"], t["qweight"].shape[1]
+                tot += N * (K - r) // 2 + 4 * N * ((K - r) // G) + 2 * N * r + 2 * K * m + 2 * N * m
+        return tot
+
+    def launches_per_step(self) -> int:
+        return (4 if self.fused else 7) * self.nlayers
+
+    # ---- one token ------------------------------------------------------------------------------
+    def _part(self, t, y):
+        return {"qweight": t["qweight"], "scales": t["scales"], "scaled_zeros": t["scaled_zeros"],
+                "oweight": t["oweight_interleaved"], "bias": t.get("bias"), "N": t["N"], "y": y}
+
+    def step_eager(self):
+        m, r, G, h, f = self.batch, self.r, self.G, self.h, self.f
+        lay = _lib.OW_INTERLEAVED
+        for li, (blk, out) in enumerate(zip(self.blocks, self.out)):
+            for gi, names in enumerate(self.groups):
+                x = self.x_f if names[0] == "down" else self.x_h
+                gather = blk["o"].get("reorder_ids32") if names[0] == "o" else None
+                if self.fused:
+                    qeft_cuda.gemv_w4_multi(x, [self._part(blk[n], out[n]) for n in names], m, x.shape[-1], r, G,
+                                            ow_layout=lay, x_gather=gather, pdl=self.pdl)
+                else:
+                    for n in names:
+                        t = blk[n]
+                        qeft_cuda.gemv_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight_interleaved"], m,
+                                          t["N"], x.shape[-1], G, ow_layout=lay, out=out[n], pdl=self.pdl,
+                                          x_gather=gather)
+                self._gather(li, gi)
+        return self.out[-1]["down"]
+
+    def capture(self):
+        """Capture one token into a CUDA graph (after a warm-up run on a side stream)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.step_eager()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step_eager()
+        self.graph = g
+        return g
+
+    def step(self):
+        if self.graph is None:
+            return self.step_eager()
+        self.graph.replay()
+        return self.out[-1]["down"]
+
+    def step_from_host(self, x_host_h: torch.Tensor, x_host_f: torch.Tensor, y_host: torch.Tensor):
+        """The end-to-end call: pinned host activations in, last projection's output back on the host."""
+        self.x_h.copy_(x_host_h, non_blocking=True)
+        self.x_f.copy_(x_host_f, non_blocking=True)
+        y = self.step()
+        y_host.copy_(y, non_blocking=True)
+        return y_host

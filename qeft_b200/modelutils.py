@@ -1,0 +1,85 @@
+"""Checkpoint schema of the packed model and of the fine-tuned outlier columns ("WCT").
+
+Byte-compatible with the reference (qeft/utils/modelutils.py:120-145, 185-198, 219-284):
+
+* packed checkpoint: ``{'model_state_dict', 'quantinfos': {name: Namespace(bits, sym, group_size, n_out,
+  reorder)}, 'packing': True, 'dtype', 'bits', 'group_size'}``
+* WCT checkpoint: ``{'oweight_state_dict': {layer_name: tensor}, 'base_path'}``
+
+Loading needs ``weights_only=False`` on torch >= 2.6 because of the Namespace objects.
+"""
+from __future__ import annotations
+
+import os
+from argparse import Namespace
+from collections import OrderedDict
+
+import torch
+
+from .qlinear import QuantLinear
+from .quant import find_layers, lm_pack, make_quant
+
+
+def load_checkpoint(path):
+    if os.path.isdir(path):
+        path = os.path.join(path, "model.pth")
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def hfmodel_to_owqmodel(model, ckpt, training=False, device="cuda:0"):
+    """Turn a freshly constructed (HF-style) model into the packed model described by ``ckpt``."""
+    if ckpt["packing"]:
+        make_quant(model, ckpt["quantinfos"])
+        model.load_state_dict(ckpt["model_state_dict"], strict=False)
+        if device not in ("cpu", None):
+            model = model.to(device)
+        for layer in find_layers(model, [QuantLinear]).values():
+            layer.set_kernel(training)
+    else:
+        model.load_state_dict(ckpt["model_state_dict"], strict=False)
+        if device not in ("cpu", None):
+            model = model.to(device)
+    return model
+
+
+def packed_checkpoint(model, quantizers, dtype=None):
+    """The dict the reference's ``save_model(packing=True)`` writes, for an already packed ``model``."""
+    first = next(iter(quantizers.values()))
+    infos = {n: Namespace(bits=q.bits, sym=getattr(q, "sym", False), group_size=getattr(q, "group_size", -1),
+                          n_out=getattr(q, "n_out", 0), reorder=getattr(q, "reorder", False))
+             for n, q in quantizers.items()}
+    return {"model_state_dict": model.state_dict(), "quantinfos": infos, "packing": True,
+            "dtype": dtype if dtype is not None else getattr(model, "dtype", torch.float16),
+            "bits": first.bits, "group_size": getattr(first, "group_size", -1)}
+
+
+def save_model(model, quantizers, save_path, packing=True, fake=False):
+    if fake:
+        raise NotImplementedError("fake-quant checkpoints are an offline-quantiser artefact (out of scope)")
+    os.makedirs(os.path.dirname(os.path.abspath(save_path)), exist_ok=True)
+    lm_pack(model, quantizers)
+    torch.save(packed_checkpoint(model, quantizers), save_path)
+
+
+def save_wctmodel(model, base_path, output_dir):
+    """Fine-tuned outlier columns only (reference: modelutils.py:270-284)."""
+    sd = OrderedDict()
+    dtype = getattr(model, "dtype", torch.float16)
+    for name, param in model.named_parameters():
+        if "oweight" in name:
+            sd[name.replace(".oweight", "")] = param.data.to(dtype)
+    os.makedirs(output_dir, exist_ok=True)
+    path = os.path.join(output_dir, "model.pth")
+    torch.save({"oweight_state_dict": sd, "base_path": os.path.abspath(base_path)}, path)
+    return path
+
+
+def replace_oweight(model, ckpt_wct):
+    """Install fine-tuned outlier columns AND refresh the interleaved GEMV copy (the reference only does
+    the first, modelutils.py:185-198, so its decode path keeps using the pre-fine-tuning columns)."""
+    sd = ckpt_wct["oweight_state_dict"]
+    for name, module in model.named_modules():
+        if isinstance(module, QuantLinear) and name in sd:
+            module.oweight.data = sd[name].data.to(device=module.oweight.device, dtype=module.oweight.dtype)
+            module.refresh_oweight_interleaved()
+    return model

@@ -1,0 +1,234 @@
+"""Python face of the C ABI with the operator signatures of the reference's ``qeft_cuda`` module.
+
+Reference boundary: ``qeft/kernel/qeft_cuda.cpp:10-27`` binds ``gemm_4bit`` (gemm/gemm_cuda.cu:929),
+``gemv_4bit`` (gemv/gemv_cuda.cu:358) and ``gemv_4bit_qeft`` (gemv/gemv_cuda_qeft.cu:392).  The three
+functions below keep those names, argument orders and meanings, allocate the output with the torch
+caching allocator like the reference (`torch::empty`) and raise ``RuntimeError`` on bad input.  Unlike
+the reference they launch on torch's *current* stream of the tensors' device, so they are
+multi-device-safe and CUDA-graph-capturable.
+
+The remaining functions are the fused B200 entry points the module layer uses (one launch per
+projection group, outliers/bias/o_proj gather inside the kernel).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_PDL_DEFAULT = True
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("qeft_b200 has no CPU path: all operands must be CUDA tensors")
+
+
+def _f16(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.float16:
+        raise RuntimeError(f"expected scalar type Half for {what} but found {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _flags(pdl: Optional[bool]) -> int:
+    return _lib.F_PDL if (_PDL_DEFAULT if pdl is None else pdl) else 0
+
+
+# ----------------------------------------------------------------------------------------------
+# reference signatures
+# ----------------------------------------------------------------------------------------------
+def gemv_4bit_qeft(in_feats, kernel, scaling_factors, zeros, oweight, m, n, k, group_size):
+    """Reference ``gemv_4bit_qeft``: ``oweight`` is the row-pair interleaved ``[N/2, 2r]`` tensor."""
+    return gemv_w4(in_feats, kernel, scaling_factors, zeros, oweight, m, n, k, group_size,
+                   ow_layout=_lib.OW_INTERLEAVED)
+
+
+def gemv_4bit(in_feats, kernel, scaling_factors, zeros, m, n, k, group_size):
+    """Reference ``gemv_4bit`` (no outlier columns)."""
+    return gemv_w4(in_feats, kernel, scaling_factors, zeros, None, m, n, k, group_size, ow_layout=_lib.OW_NONE)
+
+
+def gemm_4bit(in_feats, kernel, scales, zeros):
+    """Reference ``gemm_4bit``: all K int4 columns, no outlier term, no bias."""
+    return gemm_w4(in_feats, kernel, scales, zeros, None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused entry points
+# ----------------------------------------------------------------------------------------------
+def gemv_w4(x, qweight, scales, scaled_zeros, oweight, m, n, k, group_size, *, ow_layout, bias=None,
+            x_gather=None, out=None, pdl=None):
+    _need_cuda(x, qweight, scales, scaled_zeros, oweight, bias, x_gather)
+    x = _f16(x, "in_feats")
+    scales = _f16(scales, "scaling_factors")
+    scaled_zeros = _f16(scaled_zeros, "zeros")
+    if m < 1 or m > 8 or x.numel() != m * k:
+        raise RuntimeError("Unsupported batch size for gemv kernel.")
+    r = 0
+    if oweight is not None:
+        oweight = _f16(oweight, "oweight")
+        r = oweight.shape[1] // 2 if ow_layout == _lib.OW_INTERLEAVED else oweight.shape[1]
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (n,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.load().qeft_gemv_w4(_ptr(x), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
+                                      ow_layout, _ptr(bias), _ptr(x_gather), _ptr(out), m, n, k, r, group_size,
+                                      _flags(pdl), _stream(x))
+    _lib.check(st, "qeft_gemv_w4")
+    return out
+
+
+def gemv_w4_multi(x, parts: Sequence[dict], m, k, r, group_size, *, ow_layout, x_gather=None, pdl=None):
+    """One launch for several projections that share ``x``.  ``parts``: dicts with qweight, scales,
+    scaled_zeros, oweight, bias, N (+ optional preallocated ``y``).  Returns the list of outputs."""
+    _need_cuda(x)
+    x = _f16(x, "in_feats")
+    arr = (_lib.GemvPart * len(parts))()
+    outs = []
+    for i, p in enumerate(parts):
+        y = p.get("y")
+        if y is None:
+            y = torch.empty(x.shape[:-1] + (p["N"],), dtype=x.dtype, device=x.device)
+        outs.append(y)
+        arr[i] = _lib.GemvPart(_ptr(p["qweight"]), _ptr(p["scales"]), _ptr(p["scaled_zeros"]),
+                               _ptr(p.get("oweight")), _ptr(p.get("bias")), _ptr(y), p["N"])
+    with torch.cuda.device(x.device):
+        st = _lib.load().qeft_gemv_w4_multi(_ptr(x), arr, len(parts), ow_layout, _ptr(x_gather), m, k, r, group_size,
+                                            _flags(pdl), _stream(x))
+    _lib.check(st, "qeft_gemv_w4_multi")
+    return outs
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return _lib.DT_F16
+    if t.dtype == torch.bfloat16:
+        return _lib.DT_BF16
+    raise RuntimeError(f"expected scalar type Half or BFloat16 but found {t.dtype}")
+
+
+def gemm_w4(x, qweight, scales, scaled_zeros, oweight, bias, *, group_size=128, out=None, pdl=None):
+    """``y = x . Wdense^T (+ bias)``; ``oweight`` plain ``[N, r]`` fp16/bf16 or None (r = 0)."""
+    _need_cuda(x, qweight, scales, scaled_zeros, oweight, bias)
+    dt = _dt(x)
+    x = x if x.is_contiguous() else x.contiguous()
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = qweight.shape[0] * 4
+    r = 0 if oweight is None else oweight.shape[1]
+    if oweight is not None and not oweight.is_contiguous():
+        oweight = oweight.contiguous()
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.load().qeft_gemm_w4(_ptr(x), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
+                                      _ptr(bias), _ptr(out), M, N, K, r, group_size, dt, _flags(pdl), _stream(x))
+    _lib.check(st, "qeft_gemm_w4")
+    return out
+
+
+def gemm_w4_dx(dy, qweight, scales, scaled_zeros, oweight, K, *, group_size=128, out=None, pdl=None):
+    """``dx[M, K] = dy[M, N] . Wdense``."""
+    _need_cuda(dy, qweight, scales, scaled_zeros, oweight)
+    dt = _dt(dy)
+    dy = dy if dy.is_contiguous() else dy.contiguous()
+    N = dy.shape[-1]
+    M = dy.numel() // N
+    r = 0 if oweight is None else oweight.shape[1]
+    if out is None:
+        out = torch.empty(dy.shape[:-1] + (K,), dtype=dy.dtype, device=dy.device)
+    with torch.cuda.device(dy.device):
+        st = _lib.load().qeft_gemm_w4_dx(_ptr(dy), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
+                                         _ptr(out), M, N, K, r, group_size, dt, _flags(pdl), _stream(dy))
+    _lib.check(st, "qeft_gemm_w4_dx")
+    return out
+
+
+def dow(dy, x, r, *, out=None, accumulate=False, pdl=None):
+    """``dow[N, r] (fp32) (+)= dy^T . x[:, K-r:]``."""
+    _need_cuda(dy, x)
+    dt = _dt(dy)
+    if x.dtype != dy.dtype:
+        raise RuntimeError("dy and x must have the same dtype")
+    dy = dy if dy.is_contiguous() else dy.contiguous()
+    x = x if x.is_contiguous() else x.contiguous()
+    N, K = dy.shape[-1], x.shape[-1]
+    M = dy.numel() // N
+    if out is None:
+        out = torch.empty((N, r), dtype=torch.float32, device=dy.device)
+        accumulate = False
+    with torch.cuda.device(dy.device):
+        st = _lib.load().qeft_dow(_ptr(dy), _ptr(x), _ptr(out), M, N, K, r, dt, int(accumulate), _flags(pdl),
+                                  _stream(dy))
+    _lib.check(st, "qeft_dow")
+    return out
+
+
+def pack_w4(intweight: torch.Tensor) -> torch.Tensor:
+    """Device packer: int32 ``[N, K]`` -> int16 ``[N/4, K]`` (bit-exact with the reference's pack_intweight)."""
+    _need_cuda(intweight)
+    q = intweight.to(torch.int32).contiguous()
+    N, K = q.shape
+    out = torch.empty((N // 4, K), dtype=torch.int16, device=q.device)
+    with torch.cuda.device(q.device):
+        st = _lib.load().qeft_pack_w4(_ptr(q), _ptr(out), N, K, _stream(q))
+    _lib.check(st, "qeft_pack_w4")
+    return out
+
+
+def unpack_w4(qweight: torch.Tensor) -> torch.Tensor:
+    _need_cuda(qweight)
+    qweight = qweight.contiguous()
+    Nq, K = qweight.shape
+    out = torch.empty((Nq * 4, K), dtype=torch.int32, device=qweight.device)
+    with torch.cuda.device(qweight.device):
+        st = _lib.load().qeft_unpack_w4(_ptr(qweight), _ptr(out), Nq * 4, K, _stream(qweight))
+    _lib.check(st, "qeft_unpack_w4")
+    return out
+
+
+def dequant_w4(qweight, scales, scaled_zeros, oweight=None, group_size=128, dtype=torch.float16):
+    """Dense ``[N, K]`` weight the packed layer stands for (debug / checks; never on the hot path)."""
+    _need_cuda(qweight, scales, scaled_zeros, oweight)
+    Nq, K = qweight.shape
+    N = Nq * 4
+    r = 0 if oweight is None else oweight.shape[1]
+    out = torch.empty((N, K), dtype=dtype, device=qweight.device)
+    dt = _lib.DT_F16 if dtype == torch.float16 else _lib.DT_BF16
+    with torch.cuda.device(qweight.device):
+        st = _lib.load().qeft_dequant_w4(_ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight), _ptr(out),
+                                         N, K, r, group_size, dt, _stream(qweight))
+    _lib.check(st, "qeft_dequant_w4")
+    return out
+
+
+def interleave_oweight(oweight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``pack_oweight`` on the device; accepts the fp32 master copy used during fine-tuning."""
+    _need_cuda(oweight)
+    ow = oweight.detach()
+    if ow.dtype not in (torch.float16, torch.float32):
+        raise RuntimeError(f"oweight must be fp16 or fp32, found {ow.dtype}")
+    ow = ow if ow.is_contiguous() else ow.contiguous()
+    N, r = ow.shape
+    if out is None:
+        out = torch.empty((N // 2, 2 * r), dtype=torch.float16, device=ow.device)
+    with torch.cuda.device(ow.device):
+        st = _lib.load().qeft_interleave_oweight(_ptr(ow), _ptr(out), N, r, int(ow.dtype == torch.float32), _stream(ow))
+    _lib.check(st, "qeft_interleave_oweight")
+    return out
+
+
+def launch_count() -> int:
+    return _lib.launch_count()

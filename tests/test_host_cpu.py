@@ -1,0 +1,150 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import qeft_b200
+from qeft_b200 import _lib
+from qeft_b200.qlinear import QuantLinear, pack_intweight, pack_oweight, unpack_intweight
+from qeft_b200.quant import make_quant
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qeft_b200.h")).read()
+    declared = set(re.findall(r"QEFT_API\s+[\w\s\*]+?\b(qeft_\w+)\s*\(", hdr))
+    assert declared, "header parse failed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().qeft_abi_version() == 1
+    assert b"sm_100a" in _lib.load().qeft_build_info()
+
+
+def test_argument_validation_without_a_gpu():
+    lib = _lib.load()
+    dummy = ctypes.c_void_p(16)  # aligned non-null; never dereferenced because validation fails first
+    # NULL pointers
+    assert lib.qeft_gemv_w4(None, dummy, dummy, dummy, None, 0, None, None, dummy, 1, 64, 128, 0, 128, 0, None) == -1
+    # batch outside 1..8 -> the reference's "Unsupported batch size" error
+    st = lib.qeft_gemv_w4(dummy, dummy, dummy, dummy, None, 0, None, None, dummy, 9, 64, 128, 0, 128, 0, None)
+    assert st == -3 and b"Unsupported batch size" in lib.qeft_status_string(st)
+    # shape rules: N % 8, K % 64, r % 32
+    assert lib.qeft_gemv_w4(dummy, dummy, dummy, dummy, None, 0, None, None, dummy, 1, 60, 128, 0, 128, 0, None) == -2
+    assert lib.qeft_gemv_w4(dummy, dummy, dummy, dummy, None, 0, None, None, dummy, 1, 64, 100, 0, 100, 0, None) == -2
+    assert lib.qeft_gemv_w4(dummy, dummy, dummy, dummy, dummy, 2, None, None, dummy, 1, 64, 128, 48, 128, 0, None) == -2
+    assert lib.qeft_pack_w4(None, dummy, 8, 64, None) == -1
+    assert lib.qeft_pack_w4(dummy, dummy, 6, 64, None) == -2
+    misaligned = ctypes.c_void_p(8)
+    assert lib.qeft_gemv_w4(misaligned, dummy, dummy, dummy, None, 0, None, None, dummy, 1, 64, 128, 0, 128, 0, None) == -5
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(1, 128, dtype=torch.float16)
+    qw = torch.zeros(16, 128, dtype=torch.int16)
+    s = torch.zeros(1, 64, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        qeft_b200.qeft_cuda.gemv_4bit(x, qw, s, s, 1, 64, 128, 128)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        qeft_b200.qeft_cuda.gemm_4bit(x, qw, s, s)
+
+
+def test_product_packers_match_reference_vectors(golden):
+    for idx in range(7):
+        q = torch.tensor(golden[f"piw{idx}_q"].astype(np.int32))
+        want = golden[f"piw{idx}_packed"]
+        got = pack_intweight(q, interleave=4, kstride=64)
+        assert got.dtype == torch.int16
+        assert np.array_equal(got.numpy(), want)
+        assert np.array_equal(unpack_intweight(torch.tensor(want)).numpy(), q.numpy())
+    for idx in range(4):
+        ow = torch.tensor(golden[f"pow{idx}_ow"])
+        got = pack_oweight(ow, interleave=4)
+        assert np.array_equal(got.numpy().view(np.uint16), golden[f"pow{idx}_packed"].view(np.uint16))
+
+
+def test_sparse_to_dense_ids_matches_reference(golden):
+    for idx in range(4):
+        got = qeft_b200.sparse_to_dense_ids(torch.tensor(golden[f"s2d{idx}_ids"]), int(golden[f"s2d{idx}_K"]))
+        assert got.dtype == torch.int64
+        assert np.array_equal(got.numpy(), golden[f"s2d{idx}_dense"])
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_quantlinear_schema_and_pack_match_reference(golden, golden_schema, idx):
+    c = golden_schema[f"qlp{idx}"]["case"]
+    layer = QuantLinear(4, c["K"], c["N"], c["bias"], torch.float16, c["r"], c["G"], True, c["name"])
+    got_schema = {k: [list(v.shape), str(v.dtype)] for k, v in layer.state_dict().items()}
+    assert got_schema == golden_schema[f"qlp{idx}"]["state_dict"]
+    p = f"qlp{idx}_"
+    lin = torch.nn.Linear(c["K"], c["N"], bias=c["bias"])
+    lin.weight.data = torch.tensor(golden[p + "weight"])
+    if c["bias"]:
+        lin.bias.data = torch.tensor(golden[p + "bias"])
+    zeros = torch.tensor(golden[p + "zeros_in"]).clone()
+    layer.pack(lin, torch.tensor(golden[p + "scales_in"]), zeros, torch.tensor(golden[p + "outlieridx"]), sym=c["sym"])
+    assert np.array_equal(zeros.numpy(), golden[p + "zeros_after"])          # in-place +8 for sym, like the reference
+    assert np.array_equal(layer.qweight.numpy(), golden[p + "qweight"])
+    for k in ("scales", "scaled_zeros") + (("oweight", "oweight_interleaved") if c["r"] else ()):
+        assert np.array_equal(getattr(layer, k).numpy().view(np.uint16), golden[p + k].view(np.uint16)), k
+    if c["bias"]:
+        assert np.array_equal(layer.bias.numpy().view(np.uint16), golden[p + "bias"].view(np.uint16))
+
+
+def test_make_quant_schema_matches_reference(golden_schema):
+    import types
+
+    class Blk(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = torch.nn.Linear(256, 32, bias=False).half()
+            self.o_proj = torch.nn.Linear(256, 32, bias=False).half()
+            self.other = torch.nn.Linear(8, 8)
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = torch.nn.ModuleList([Blk(), Blk()])
+            self.lm_head = torch.nn.Linear(32, 16)
+
+    tiny = Tiny()
+    infos = {f"layers.{i}.{n}": types.SimpleNamespace(bits=4, n_out=128, group_size=128, reorder=True)
+             for i in range(2) for n in ("q_proj", "o_proj")}
+    make_quant(tiny, infos)
+    got = {k: [list(v.shape), str(v.dtype)] for k, v in tiny.state_dict().items()}
+    assert got == golden_schema["make_quant"]
+    assert tiny.layers[1].o_proj.name == "layers.1.o_proj"
+
+
+def test_checkpoint_roundtrip_schema(tmp_path):
+    from argparse import Namespace
+    from qeft_b200 import modelutils
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = torch.nn.Linear(256, 32, bias=False).half()
+            self.dtype = torch.float16
+
+    m = M()
+    qinfo = {"q_proj": Namespace(bits=4, n_out=128, group_size=128, reorder=True, sym=False,
+                                 scale_group=torch.rand(32, 2).half() * 0.01 + 0.002,
+                                 zero_group=torch.randint(0, 16, (32, 2)).half(),
+                                 out_ids=torch.arange(128, 256, dtype=torch.int32))}
+    path = str(tmp_path / "ckpt" / "packed.pth")
+    modelutils.save_model(m, qinfo, path, packing=True, fake=False)
+    ck = modelutils.load_checkpoint(path)
+    assert set(ck) == {"model_state_dict", "quantinfos", "packing", "dtype", "bits", "group_size"}
+    assert ck["packing"] is True and ck["bits"] == 4 and ck["group_size"] == 128
+    assert vars(ck["quantinfos"]["q_proj"]) == dict(bits=4, sym=False, group_size=128, n_out=128, reorder=True)
+    m2 = M()
+    make_quant(m2, ck["quantinfos"])
+    missing, unexpected = m2.load_state_dict(ck["model_state_dict"], strict=False)
+    assert not missing and not unexpected
+    assert torch.equal(m2.q_proj.qweight, m.q_proj.qweight)
