@@ -222,8 +222,10 @@ gemv_w4_kernel(const GemvParams p) {
       const int gi = i / per_group, q = i - gi * per_group;
       const int oct = q >> 1, which = q & 1;                // rows 8 oct .. 8 oct + 7; scales / scaled zeros
       const __half* src = (which ? P.szeros : P.scales) + (size_t)gi * N + n0 + 8 * oct;
-      *reinterpret_cast<uint4*>(sctab + (gi * RG + (oct >> 1)) * 32 + which * 16 + 8 * (oct & 1)) = ldg_nc_v4(src);
+      const uint32_t dst = smem_u32(sctab + (gi * RG + (oct >> 1)) * 32 + which * 16 + 8 * (oct & 1));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   pdl_wait();   // x (and y as a reused buffer) belong to the previous kernel until here
@@ -284,7 +286,72 @@ gemv_w4_kernel(const GemvParams p) {
     for (int i = tid; i < nsteps * 8; i += kConsumers)
       if ((i & 7) >= m) { xsum[i] = 0.f; csum[i] = 0.f; }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");     // scale table
   named_bar_sync(1, kConsumers);
+
+  // ---- outlier columns (CUDA cores, fp32), reduced with warp shuffles ---------------------------
+  if (r > 0) {
+    const __half* xo = (XS ? xs : xg) + (K - r);
+#pragma unroll
+    for (int it = 0; it < kMaxOwIters; ++it) {
+      const int piece = tid + it * kConsumers;
+      if (it > 0 && it * kConsumers >= npieces) break;   // uniform
+      const bool live = piece < npieces;
+      const uint32_t w4[4] = {owv[it].x, owv[it].y, owv[it].z, owv[it].w};
+      if (p.ow_layout == QEFT_OW_INTERLEAVED) {
+        // interleaved row R (local) holds rows nl and nl+4; 16 bytes = columns j0..j0+3 of both rows
+        const int per_row = r >> 2;                 // pieces per interleaved row
+        const int R = live ? piece / per_row : 0, pp = live ? piece - R * per_row : 0;
+        const int c = pp >> 3, j0 = 32 * c + 4 * (pp & 7);
+        const int nl = 8 * (R >> 2) + (R & 3);
+        for (int b = 0; b < m; ++b) {
+          float s0 = 0.f, s1 = 0.f;
+          if (live) {
+            uint2 xv = XS ? *reinterpret_cast<const uint2*>(xo + (size_t)b * xstride + j0)
+                          : ldg_nc_v2(xo + (size_t)b * xstride + j0);
+            const float2 x01 = half2_bits_to_float2(xv.x), x23 = half2_bits_to_float2(xv.y);
+            const float xf[4] = {x01.x, x01.y, x23.x, x23.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 wv = half2_bits_to_float2(w4[j]);   // {row nl, row nl+4} at column j0+j
+              s0 = fmaf(wv.x, xf[j], s0);
+              s1 = fmaf(wv.y, xf[j], s1);
+            }
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 4); s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+          if (live && (pp & 7) == 0) {
+            opart[(c * kRows + nl) * 8 + b] = s0;
+            opart[(c * kRows + nl + 4) * 8 + b] = s1;
+          }
+        }
+      } else {
+        // plain [N, r]: 16 bytes = 8 consecutive columns of one row
+        const int per_row = r >> 3;
+        const int nl = live ? piece / per_row : 0, pp = live ? piece - nl * per_row : 0;
+        const int c = pp >> 2, j0 = 8 * pp;
+        for (int b = 0; b < m; ++b) {
+          float s0 = 0.f;
+          if (live) {
+            uint4 xv = XS ? *reinterpret_cast<const uint4*>(xo + (size_t)b * xstride + j0)
+                          : ldg_nc_v4(xo + (size_t)b * xstride + j0);
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 wv = half2_bits_to_float2(w4[j]);
+              const float2 xf = half2_bits_to_float2(xw[j]);
+              s0 = fmaf(wv.x, xf.x, s0);
+              s0 = fmaf(wv.y, xf.y, s0);
+            }
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+          if (live && (pp & 3) == 0) opart[(c * kRows + nl) * 8 + b] = s0;
+        }
+      }
+    }
+  }
 
   // ---- main loop ------------------------------------------------------------------------------
   float yacc[RG][4];                       // per row group: rows g, g+8 x batch columns 2t, 2t+1
@@ -394,70 +461,6 @@ gemv_w4_kernel(const GemvParams p) {
         const uint4 vb = ldg_stream_v4(P.qw + (size_t)qb * (size_t)(2 * K) + inrow);
         const float mine = __half2float(my_sc[(grp * RG + q) * 32]);
         step_math(yacc[q], va, vb, xb, mine, xs2, cs2);
-      }
-    }
-  }
-
-  // ---- outlier columns (CUDA cores, fp32), reduced with warp shuffles ---------------------------
-  if (r > 0) {
-    const __half* xo = (XS ? xs : xg) + (K - r);
-#pragma unroll
-    for (int it = 0; it < kMaxOwIters; ++it) {
-      const int piece = tid + it * kConsumers;
-      if (it > 0 && it * kConsumers >= npieces) break;   // uniform
-      const bool live = piece < npieces;
-      const uint32_t w4[4] = {owv[it].x, owv[it].y, owv[it].z, owv[it].w};
-      if (p.ow_layout == QEFT_OW_INTERLEAVED) {
-        // interleaved row R (local) holds rows nl and nl+4; 16 bytes = columns j0..j0+3 of both rows
-        const int per_row = r >> 2;                 // pieces per interleaved row
-        const int R = live ? piece / per_row : 0, pp = live ? piece - R * per_row : 0;
-        const int c = pp >> 3, j0 = 32 * c + 4 * (pp & 7);
-        const int nl = 8 * (R >> 2) + (R & 3);
-        for (int b = 0; b < m; ++b) {
-          float s0 = 0.f, s1 = 0.f;
-          if (live) {
-            uint2 xv = XS ? *reinterpret_cast<const uint2*>(xo + (size_t)b * xstride + j0)
-                          : ldg_nc_v2(xo + (size_t)b * xstride + j0);
-            const float2 x01 = half2_bits_to_float2(xv.x), x23 = half2_bits_to_float2(xv.y);
-            const float xf[4] = {x01.x, x01.y, x23.x, x23.y};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wv = half2_bits_to_float2(w4[j]);   // {row nl, row nl+4} at column j0+j
-              s0 = fmaf(wv.x, xf[j], s0);
-              s1 = fmaf(wv.y, xf[j], s1);
-            }
-          }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 4); s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-          if (live && (pp & 7) == 0) {
-            opart[(c * kRows + nl) * 8 + b] = s0;
-            opart[(c * kRows + nl + 4) * 8 + b] = s1;
-          }
-        }
-      } else {
-        // plain [N, r]: 16 bytes = 8 consecutive columns of one row
-        const int per_row = r >> 3;
-        const int nl = live ? piece / per_row : 0, pp = live ? piece - nl * per_row : 0;
-        const int c = pp >> 2, j0 = 8 * pp;
-        for (int b = 0; b < m; ++b) {
-          float s0 = 0.f;
-          if (live) {
-            uint4 xv = XS ? *reinterpret_cast<const uint4*>(xo + (size_t)b * xstride + j0)
-                          : ldg_nc_v4(xo + (size_t)b * xstride + j0);
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wv = half2_bits_to_float2(w4[j]);
-              const float2 xf = half2_bits_to_float2(xw[j]);
-              s0 = fmaf(wv.x, xf.x, s0);
-              s0 = fmaf(wv.y, xf.y, s0);
-            }
-          }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-          if (live && (pp & 3) == 0) opart[(c * kRows + nl) * 8 + b] = s0;
-        }
       }
     }
   }
