@@ -3,26 +3,35 @@
 // Replaces gemv_kernel / gemv_kernel_qeft of the reference
 // (qeft/kernel/quantization_new/gemv/gemv_cuda.cu:73-204, gemv_cuda_qeft.cu:75-222).
 //
-// Design (see DESIGN.md "GEMV"):
-//   * one CTA = RG x 16 output rows (RG x 4 consecutive qweight rows) x all of K; W = 4 consumer warps + 1
-//     producer warp.  Consumer warp w owns the 128-column k-steps w, w+W, ... of every row group.
-//   * the producer warp streams the CTA's packed bytes into a shared-memory ring with 1-D bulk async copies
-//     (cp.async.bulk, completion on an mbarrier): one ring stage = one "round" of 8 k-steps = 2 KB of
-//     contiguous bytes from each qweight row.  Many stages are in flight per CTA without costing a
-//     register.  x itself arrives by one bulk copy per batch row.  The weight stream never waits for the
-//     previous kernel: with programmatic dependent launch the weights of layer i+1 stream in while layer i
-//     drains (weights do not depend on the previous kernel's output); only the x copy waits.
-//   * a consumer thread reads its two 16-byte chunks (32 nibbles of row g and of row g+8) from the ring and
-//     turns every nibble pair into an fp16 pair with ONE lop3 (the nibble is OR-ed into the mantissa of
-//     1024.0, giving 1024+q or 1024+16q exactly).  These go, without any shuffle or conversion, into the A
-//     fragment of mma.m16n8k16 (the packed order IS that fragment order); x is the B fragment (batch
-//     m <= 8 columns); accumulation is fp32 in two chains, one per nibble position, and the 1024 bias is
-//     removed per 128-column group with the group's x sums:
+// Design (see DESIGN.md "GEMV"; the measurements behind it are in profiles/r01_microbench_stream.md):
+//   * persistent grid, one 8-warp CTA per SM.  The qweight rows (4 output rows each) of all projections of the
+//     launch are split evenly over the CTAs (balance to one qweight row: 4096 rows over 148 SMs is 6 or 7 per
+//     CTA), so every SM streams the same number of bytes and the whole chip finishes together.
+//   * a CTA walks its rows as 16-row tiles (4 qweight rows; tiles are aligned to 16 rows of the projection, a
+//     CTA streams only the qweight rows it owns of a boundary tile).  A tile's work is cut into units of two
+//     128-column steps (int4) or two 32-column steps (fp16 outlier columns); unit u goes to warp u % 8.
+//   * every lane prefetches exactly the 16-byte chunks it will itself consume with cp.async (LDGSTS) into a
+//     lane-private shared-memory ring, D units deep (~90 KB in flight per SM): no producer warp, no barrier on
+//     the data path, no registers tied up by loads in flight.  (1-D bulk copies were measured first: they need
+//     >= 8 KB per operation to reach HBM speed, this layout's contiguous pieces are 256 B.)  The ring is filled
+//     BEFORE griddepcontrol.wait, so under programmatic dependent launch the next kernel's weights stream in
+//     while this kernel computes; only x waits for the previous kernel.
+//   * a lane turns every nibble pair into an fp16 pair with ONE lop3 (the nibble is OR-ed into the mantissa of
+//     1024.0, giving 1024+q or 1024+16q exactly).  These are, without any shuffle, the A fragment of
+//     mma.m16n8k16 (the packed order IS that fragment order); x is the B fragment (batch m <= 8 columns);
+//     accumulation is fp32 in two chains, one per nibble position, and the 1024 bias is removed per
+//     128-column step with the step's x sums:
 //         sum(q x) = acc_lo + acc_hi / 16 - (1024 sum_lo(x) + 64 sum_hi(x))
-//         y += s * sum(q x) + sz * sum(x)                       (fp32, once per group)
-//   * the fp16 outlier columns are a CUDA-core dot product reduced with warp shuffles; the k-split
-//     partial sums of the warps meet in shared memory; fp16 store.
+//         y += s * sum(q x) + sz * sum(x)                       (fp32, once per step)
+//   * the fp16 outlier columns go through the same MMA (either layout: plain [N, r] or the reference's
+//     row-pair interleaved [N/2, 2r], regrouped with byte permutes).  Accumulator row "g" of a lane is tile row
+//     8 (g/4) + g%4 and row "g+8" is that + 4, which is the interleaved layout's own row pairing.
+//   * each warp keeps a tile's partial sums in registers and writes them once to its own shared-memory slice;
+//     after a CTA barrier the slices are added in a fixed order (deterministic), bias is added, and the CTA's
+//     owned rows are stored as fp16.
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace qeft {
 
@@ -36,7 +45,7 @@ struct GemvPart {
   const __half* bias;     // [N] or null
   __half* y;              // [m, N]
   int N;
-  int cta_begin;          // first blockIdx.x of this part
+  int q_begin;            // first qweight row of this part in the launch-wide numbering
 };
 
 struct GemvParams {
@@ -48,43 +57,57 @@ struct GemvParams {
   int g128;               // G / 128 (1 for the common G = 128), 0 for per-channel scales (G == K)
   int ow_layout;
   int nsteps;             // ceil((K - r) / 128)
-  int nfull;              // (K - r) / 128: steps whose four 32-column chunks are all live
   int nchunks;            // (K - r) / 32 live 32-column chunks
-  int xstride;            // halves between batch rows of the staged x (K + 8: rows start 4 banks apart)
-  int ngroups;            // scale groups that cover the live int4 columns
-  int stages;             // ring depth (rounds in flight)
-  int rounds;             // ceil(nfull / consumer warps)
-  int pdl;                // launched with programmatic dependent launch: x is not ready when the CTA starts
+  int nku;                // int4 units per tile = ceil(nsteps / 2)
+  int nou;                // outlier units per tile = ceil(r / 64)
+  int xstride;            // halves between batch rows of the staged x (128 nsteps + 32: rows start 16 banks apart)
+  int q_lo, q_hi;         // window of launch-wide qweight rows this launch covers
+  int max_tiles;          // upper bound of tiles per CTA (sizes the partial-sum slices)
 };
 
-// ---- mbarrier / bulk-copy primitives (shared::cta addresses as 32-bit) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+  return r;
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// predicated forms: no branch, lanes with p == false do not touch shared memory (their outputs are undefined)
+__device__ __forceinline__ uint4 lds_v4_if(uint32_t a, int p) {
+  uint4 r;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a), "r"(p) : "memory");
+  return r;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
+__device__ __forceinline__ uint2 lds_v2_if(uint32_t a, int p) {
+  uint2 r;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0,%1}, [%2];\n\t}"
+               : "=r"(r.x), "=r"(r.y) : "r"(a), "r"(p) : "memory");
+  return r;
 }
-// global -> shared 1-D bulk copy, bytes multiple of 16, completion counted on `bar`
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, int p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+               ::"r"(dst), "l"(src), "r"(p) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ float lds_h(uint32_t a) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a) : "memory");
+  return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
 
 // mma with a zero accumulator input (first k-slice of a chain)
@@ -108,148 +131,166 @@ __device__ __forceinline__ void unpack_word_biased(uint32_t w, uint32_t (&h)[4])
   asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(h[3]) : "r"(t), "n"(kHi), "n"(kMagic));
 }
 
-constexpr int kStepBytes = 256;                       // one qweight row's bytes of a 128-column step
-constexpr int kMaxStages = 16;
+constexpr int kStepBytes = 256;                 // one qweight row's bytes of a 128-column step
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kSlotBytes = 4 * 512 + 128;       // per warp and unit: 4 chunks of 16 B per lane + 2 steps x (16 s | 16 z)
 
-// RG: 16-row groups per CTA (1 or 2).  XS: x staged in shared memory.  G128: one scale group per k-step.
-template <int WARPS, int RG, bool XS, bool G128, int MINB>
-__global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
+// tiles [t0, t0 + nt) of part `part` (ordinals cum .. cum + nt in this CTA); the CTA owns the part-local qweight
+// rows [pa, pb)
+struct Seg { int part, t0, nt, pa, pb, cum; };
+
+// D: ring depth in units per warp.  XS: x staged in shared memory (otherwise read through L1/L2 at every use)
+template <int D, bool XS>
+__global__ void __launch_bounds__(kThreads, 2)
 gemv_w4_kernel(const GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int kConsumers = WARPS * 32;
-  constexpr int kRowBytes = WARPS * kStepBytes;          // one round of one qweight row
-  constexpr int kStageBytes = RG * 4 * kRowBytes;        // RG x 4 qweight rows
-  constexpr int kRows = RG * 16;
+  __shared__ Seg segs[QEFT_GEMV_MAX_PARTS];
+  __shared__ int s_nseg, s_ntiles;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-
-  // ---- which part / which rows ------------------------------------------------------------
-  int pi = 0;
-#pragma unroll
-  for (int i = 1; i < QEFT_GEMV_MAX_PARTS; ++i)
-    if (i < p.nparts && (int)blockIdx.x >= p.part[i].cta_begin) pi = i;
-  const GemvPart& P = p.part[pi];
-  const int n0 = ((int)blockIdx.x - P.cta_begin) * kRows;
-  const int N = P.N, K = p.K, r = p.r, m = p.m;
-  const int nsteps = p.nsteps, nchunks = p.nchunks, nfull = p.nfull;
-  const int stages = p.stages, rounds = p.rounds;
-  const int live_rows = min(kRows, N - n0);          // multiple of 8 (N % 8 == 0)
-  const int live_q = live_rows >> 2;                 // live qweight rows (multiple of 2)
+  const int ra = 8 * (g >> 2) + (g & 3), rb = ra + 4;   // tile rows of this lane's two accumulator rows
+  const int K = p.K, r = p.r, m = p.m;
+  const int nsteps = p.nsteps, nchunks = p.nchunks;
+  const int nku = p.nku, upt = p.nku + p.nou;
+  const bool inter = p.ow_layout == QEFT_OW_INTERLEAVED;
 
   // ---- shared memory carve-up -----------------------------------------------------------
-  uint8_t* ring = smem_raw;                                                   // [stages][kStageBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kStageBytes);   // full[16], empty[16], xbar
-  float* red = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2);           // [WARPS][kRows][8]
-  float* xsum = red + WARPS * kRows * 8;                                      // [nsteps][8]  sum(x) per k-step
-  float* csum = xsum + nsteps * 8;                                            // [nsteps][8]  1024 sum_lo(x) + 64 sum_hi(x)
-  float* opart = csum + nsteps * 8;                                           // [r/32][kRows][8] outlier partial sums
-  __half* sctab = reinterpret_cast<__half*>(opart + (r >> 5) * kRows * 8);    // [ngroups][RG][16 scales | 16 scaled zeros]
-  __half* xs = sctab + (size_t)p.ngroups * RG * 32;                           // staged x [m][xstride]
-  const uint32_t ring_u32 = smem_u32(ring);
-  const uint32_t full_u32 = smem_u32(bars), empty_u32 = smem_u32(bars + kMaxStages);
-  const uint32_t xbar_u32 = smem_u32(bars + 2 * kMaxStages);
-  const bool x_by_bulk = XS && (p.gather == nullptr);
+  uint8_t* ring = smem_raw;                                                      // [warps][D][kSlotBytes]
+  float* part = reinterpret_cast<float*>(ring + (size_t)kWarps * D * kSlotBytes);   // [max_tiles][warps][16][m]
+  float4* sums = reinterpret_cast<float4*>(part + (size_t)p.max_tiles * kWarps * 16 * m);
+                                                         // [nsteps][4]: batch columns 2t, 2t+1: {sum x, sum x, c, c}
+  __half* xs = reinterpret_cast<__half*>(sums + nsteps * 4);                     // staged x [m][xstride], dead columns zeroed
+  __half* xo = xs + (XS ? (size_t)m * p.xstride : 0);                            // staged outlier activations [m][r]
+  const uint32_t ring_u32 = smem_u32(ring) + (uint32_t)(warp * D * kSlotBytes);
 
   if (tid == 0) {
-    for (int i = 0; i < stages; ++i) {
-      mbar_init(full_u32 + 8 * i, 1);
-      mbar_init(empty_u32 + 8 * i, WARPS);
+    // the CTA's share of the launch's qweight rows, cut into per-part tile runs
+    const long span = p.q_hi - p.q_lo;
+    const int qa = p.q_lo + (int)(((long)blockIdx.x * span) / gridDim.x);
+    const int qb = p.q_lo + (int)(((long)(blockIdx.x + 1) * span) / gridDim.x);
+    int ns = 0, cum = 0;
+    for (int i = 0; i < p.nparts; ++i) {
+      const int b = p.part[i].q_begin, e = b + (p.part[i].N >> 2);
+      const int lo = max(qa, b), hi = min(qb, e);
+      if (lo < hi) {
+        Seg s;
+        s.part = i; s.pa = lo - b; s.pb = hi - b;
+        s.t0 = s.pa >> 2; s.nt = ((s.pb + 3) >> 2) - s.t0; s.cum = cum;
+        cum += s.nt;
+        segs[ns++] = s;
+      }
     }
-    mbar_init(xbar_u32, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_nseg = ns; s_ntiles = cum;
   }
   __syncthreads();
   pdl_launch_dependents();
+  const int nseg = s_nseg, ntiles = s_ntiles;
+  const int nunits = ntiles * upt;
+  // this warp's contiguous run of units [u0, u1) of the CTA's (tile, unit-in-tile) sequence
+  const int u0 = (int)(((long)warp * nunits) / kWarps), u1 = (int)(((long)(warp + 1) * nunits) / kWarps);
 
-  // =====================================================================================================
-  // producer warp
-  // =====================================================================================================
-  if (warp == WARPS) {
-    const uint8_t* qrow0 = P.qw + (size_t)(n0 >> 2) * (size_t)(2 * K);
-    bool x_sent = !x_by_bulk;
-    auto send_x = [&]() {
-      x_sent = true;
-      pdl_wait();            // x belongs to the previous kernel until here
-      if (lane == 0) mbar_expect_tx(xbar_u32, (uint32_t)(m * K * 2));
-      __syncwarp();
-      if (lane < m)
-        bulk_g2s(smem_u32(xs + (size_t)lane * p.xstride), p.x + (size_t)lane * K, (uint32_t)(K * 2), xbar_u32);
-    };
-    if (!x_sent && !p.pdl) send_x();   // x is ready: fetch it ahead of the weight stream
-    for (int rd = 0; rd < rounds; ++rd) {
-      const int st = rd % stages;
-      if (rd >= stages) {
-        if (!x_sent) send_x();     // the ring is full: fetch x before waiting for the consumers
-        mbar_wait(empty_u32 + 8 * st, (uint32_t)((rd / stages - 1) & 1));
-      }
-      const int steps = min(WARPS, nfull - rd * WARPS);
-      const uint32_t fb = full_u32 + 8 * st;
-      const uint32_t sbase = ring_u32 + (uint32_t)st * kStageBytes;
-      if (lane == 0) mbar_expect_tx(fb, (uint32_t)(live_q * steps * kStepBytes));
-      __syncwarp();
-      if (lane < live_q)
-        bulk_g2s(sbase + lane * kRowBytes, qrow0 + (size_t)lane * (size_t)(2 * K) + (size_t)rd * kRowBytes,
-                 (uint32_t)(steps * kStepBytes), fb);
-    }
-    if (!x_sent) send_x();
-    return;
-  }
-
-  // =====================================================================================================
-  // consumer warps
-  // =====================================================================================================
-  // outlier weights of this CTA: live_rows x r fp16 in 16-byte pieces (r = 128, 16 rows -> one per thread)
-  constexpr int kMaxOwIters = (32 * kRows) / kConsumers;   // r <= 256: at most 32 pieces per row
-  const int npieces = (r * live_rows) >> 3;
-  uint4 owv[kMaxOwIters];
+  // ---- prefetch side -------------------------------------------------------------------------------
+  // cached per tile: global sources of this lane
+  const uint8_t* pf_w = nullptr;     // row ra's chunk t of step 0 (row rb: + one qweight row)
+  const __half* pf_sc = nullptr;     // lanes 0..7: scale / scaled-zero source of step (lane / 4) at group 0
+  const __half* pf_ow = nullptr;     // outlier source of this lane at column 0
+  int pf_ownA = 0, pf_ownB = 0, pf_sc_ok = 0;
+  size_t pf_sc_step = 0;             // halves between consecutive steps' scale rows (G = 128: N)
+  auto pf_set_tile = [&](int tord) {
+    int sg = 0;
 #pragma unroll
-  for (int it = 0; it < kMaxOwIters; ++it) {
-    const int piece = tid + it * kConsumers;
-    owv[it] = make_uint4(0, 0, 0, 0);
-    if (piece < npieces) {
-      const uint8_t* base = (p.ow_layout == QEFT_OW_INTERLEAVED)
-                                ? reinterpret_cast<const uint8_t*>(P.ow) + (size_t)(n0 >> 1) * (size_t)(4 * r)
-                                : reinterpret_cast<const uint8_t*>(P.ow) + (size_t)n0 * (size_t)(2 * r);
-      owv[it] = ldg_stream_v4(base + (size_t)piece * 16);
+    for (int j = 1; j < QEFT_GEMV_MAX_PARTS; ++j)
+      if (j < nseg && tord >= segs[j].cum) sg = j;
+    const Seg S = segs[sg];
+    const GemvPart& P = p.part[S.part];
+    const int T = S.t0 + tord - S.cum;
+    const int qA = 4 * T + 2 * (g >> 2);
+    pf_ownA = qA >= S.pa && qA < S.pb;
+    pf_ownB = qA + 1 >= S.pa && qA + 1 < S.pb;
+    pf_w = P.qw + (size_t)qA * (size_t)(2 * K) + (size_t)((t >> 1) * 128 + (g & 3) * 32 + (t & 1) * 16);
+    const int which = (lane >> 1) & 1, half8 = lane & 1;
+    pf_sc = (which ? P.szeros : P.scales) + 16 * T + 8 * half8;
+    pf_sc_ok = lane < 8 && (16 * T + 8 * half8) < P.N;
+    pf_sc_step = (size_t)P.N;
+    if (inter)
+      pf_ow = P.ow + (size_t)(8 * T + 4 * (g >> 2) + (g & 3)) * (size_t)(2 * r) + 8 * t;
+    else
+      pf_ow = P.ow + (size_t)(16 * T + ra) * (size_t)r + 8 * t;
+  };
+  // issue the copies of unit `su` of the cached tile into `slot` (predicated copies, no divergent branches)
+  auto issue = [&](uint32_t slot, int su) {
+    const uint32_t mine = slot + lane * 16;
+    if (su < nku) {
+      const uint8_t* a = pf_w + (size_t)su * (2 * kStepBytes);
+      const uint8_t* b = a + (size_t)(2 * K);
+      const int c0 = 8 * su + t;                    // this lane's 32-column chunk of the unit's first step
+      const int l0 = c0 < nchunks, l1 = c0 + 4 < nchunks;
+      cp_async16_if(mine, a, pf_ownA & l0);
+      cp_async16_if(mine + 512, b, pf_ownB & l0);
+      cp_async16_if(mine + 1024, a + kStepBytes, pf_ownA & l1);
+      cp_async16_if(mine + 1536, b + kStepBytes, pf_ownB & l1);
+      const int s = 2 * su + (lane >> 2);
+      int grp = s;
+      if (p.g128 != 1) grp = p.g128 == 0 ? 0 : s / p.g128;       // uniform
+      cp_async16_if(slot + 2048 + lane * 16, pf_sc + (size_t)grp * pf_sc_step, pf_sc_ok & (int)(s < nsteps));
+    } else {
+      const int c0 = 64 * (su - nku);               // first outlier column of the unit
+      if (inter) {
+        // one interleaved row holds rows ra and rb: 16 bytes = 4 columns of both
+        const __half* a = pf_ow + 2 * c0;
+        const int own = pf_ownA | pf_ownB;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp_async16_if(mine + j * 512, a + 32 * j, own & (int)(c0 + 16 * j < r));
+      } else {
+        const __half* a = pf_ow + c0;
+        const __half* b = a + (size_t)(4 * r);
+#pragma unroll
+        for (int si = 0; si < 2; ++si) {
+          const int l = c0 + 32 * si < r;
+          cp_async16_if(mine + (2 * si) * 512, a + 32 * si, pf_ownA & l);
+          cp_async16_if(mine + (2 * si + 1) * 512, b + 32 * si, pf_ownB & l);
+        }
+      }
     }
-  }
-  // scale table: per (group, row group) 16 scales | 16 scaled zeros; one 16-byte load per 8 rows
-  {
-    const int per_group = live_rows >> 2;                   // 16-byte pieces per group: (live_rows / 8) x {s, z}
-    const int npc = p.ngroups * per_group;
-    for (int i = tid; i < npc; i += kConsumers) {
-      const int gi = i / per_group, q = i - gi * per_group;
-      const int oct = q >> 1, which = q & 1;                // rows 8 oct .. 8 oct + 7; scales / scaled zeros
-      const __half* src = (which ? P.szeros : P.scales) + (size_t)gi * N + n0 + 8 * oct;
-      const uint32_t dst = smem_u32(sctab + (gi * RG + (oct >> 1)) * 32 + which * 16 + 8 * (oct & 1));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  };
+
+  // fill the ring: the first D units of this warp (weights do not depend on the previous kernel)
+  int pu = u0;                         // next unit to prefetch
+  int ptord = u0 / upt, psu = u0 - ptord * upt;
+  if (u0 < u1) pf_set_tile(ptord);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    if (pu < u1) {
+      issue(ring_u32 + d * kSlotBytes, psu);
+      ++pu;
+      if (++psu == upt) { psu = 0; ++ptord; if (pu < u1) pf_set_tile(ptord); }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_commit();                 // always: the group count is the clock
   }
+
+  // zero the partial-sum slices (a warp without a unit in a tile contributes zero)
+  for (int i = tid; i < ntiles * kWarps * 16 * m; i += kThreads) part[i] = 0.f;
 
   pdl_wait();   // x (and y as a reused buffer) belong to the previous kernel until here
 
-  // ---- x: per-step sums (and, when not bulk-copied, the staged copy) ---------------------------------
+  // ---- x: staged copy and per-step sums ---------------------------------------------------------------
   const __half* xg = p.x;
-  const int xstride = XS ? p.xstride : K;
   {
-    if (x_by_bulk) mbar_wait(xbar_u32, 0);
     // units of 16 halves; 8 consecutive units = one 128-column step.  Inside a unit the first 8 halves sit in
     // "low nibble" k-slots (k % 16 < 8) and the last 8 in "high nibble" slots.
-    const int upr = cdiv(K, 128) * 8;                       // units per batch row, padded to whole steps
+    const int upr = nsteps * 8;                             // units per batch row that the int4 steps touch
     const int live_k = nchunks * 32;
+    float* sums_f = reinterpret_cast<float*>(sums);
     for (int b = 0; b < m; ++b) {
       const __half* xrow = xg + (size_t)b * K;
-      for (int u = tid; u < ((upr + 31) & ~31); u += kConsumers) {   // whole warps enter together (full-mask shuffles)
+      for (int u = tid; u < ((upr + 31) & ~31); u += kThreads) {   // whole warps enter together (full-mask shuffles)
         const int k = u * 16;
         float lo = 0.f, hi = 0.f;
-        if (k < K) {
-          uint4 v0, v1;
-          if (x_by_bulk) {
-            v0 = *reinterpret_cast<const uint4*>(xs + (size_t)b * xstride + k);
-            v1 = *reinterpret_cast<const uint4*>(xs + (size_t)b * xstride + k + 8);
-          } else {
+        if (u < upr) {
+          uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+          if (k < live_k) {                                  // live_k is a multiple of 32: whole units
             if (XS && p.gather) {
               __half tmp[16];
 #pragma unroll
@@ -260,12 +301,6 @@ gemv_w4_kernel(const GemvParams p) {
               v0 = ldg_nc_v4(xrow + k);
               v1 = ldg_nc_v4(xrow + k + 8);
             }
-            if (XS) {
-              *reinterpret_cast<uint4*>(xs + (size_t)b * xstride + k) = v0;
-              *reinterpret_cast<uint4*>(xs + (size_t)b * xstride + k + 8) = v1;
-            }
-          }
-          if (k < live_k) {
             const float2 a0 = half2_bits_to_float2(v0.x), a1 = half2_bits_to_float2(v0.y);
             const float2 a2 = half2_bits_to_float2(v0.z), a3 = half2_bits_to_float2(v0.w);
             const float2 c0 = half2_bits_to_float2(v1.x), c1 = half2_bits_to_float2(v1.y);
@@ -273,103 +308,99 @@ gemv_w4_kernel(const GemvParams p) {
             lo = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
             hi = ((c0.x + c0.y) + (c1.x + c1.y)) + ((c2.x + c2.y) + (c3.x + c3.y));
           }
+          if (XS) {
+            // dead columns of the last step are staged as zeros.  Inside a step the 8-column piece j of 32-column
+            // chunk t sits at halves 32 j + 8 t, so that the four lanes t of one fragment load read 64 contiguous bytes.
+            const int tt = (k & 127) >> 5, j0 = (k & 31) >> 3;
+            __half* d = xs + (size_t)b * p.xstride + (k & ~127) + 8 * tt;
+            *reinterpret_cast<uint4*>(d + 32 * j0) = v0;
+            *reinterpret_cast<uint4*>(d + 32 * (j0 + 1)) = v1;
+          }
         }
         lo += __shfl_xor_sync(0xffffffffu, lo, 4); hi += __shfl_xor_sync(0xffffffffu, hi, 4);
         lo += __shfl_xor_sync(0xffffffffu, lo, 2); hi += __shfl_xor_sync(0xffffffffu, hi, 2);
         lo += __shfl_xor_sync(0xffffffffu, lo, 1); hi += __shfl_xor_sync(0xffffffffu, hi, 1);
-        if ((u & 7) == 0 && (u >> 3) < nsteps) {
-          xsum[(u >> 3) * 8 + b] = lo + hi;
-          csum[(u >> 3) * 8 + b] = fmaf(1024.f, lo, 64.f * hi);
+        if ((u & 7) == 0 && u < upr) {
+          // float4 slot b/2 of the step: {X(2t), X(2t+1), C(2t), C(2t+1)}
+          float* d = sums_f + ((u >> 3) * 4 + (b >> 1)) * 4 + (b & 1);
+          d[0] = lo + hi;
+          d[2] = fmaf(1024.f, lo, 64.f * hi);
+        }
+      }
+      if (XS && r > 0) {                                     // the outlier activations
+        for (int j = tid; j < (r >> 3); j += kThreads) {
+          uint4 v;
+          if (p.gather) {
+            __half tmp[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) tmp[e] = xrow[p.gather[K - r + 8 * j + e]];
+            v = *reinterpret_cast<uint4*>(tmp);
+          } else {
+            v = ldg_nc_v4(xrow + K - r + 8 * j);
+          }
+          *reinterpret_cast<uint4*>(xo + (size_t)b * r + 8 * j) = v;
         }
       }
     }
-    for (int i = tid; i < nsteps * 8; i += kConsumers)
-      if ((i & 7) >= m) { xsum[i] = 0.f; csum[i] = 0.f; }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");     // scale table
-  named_bar_sync(1, kConsumers);
-
-  // ---- outlier columns (CUDA cores, fp32), reduced with warp shuffles ---------------------------
-  if (r > 0) {
-    const __half* xo = (XS ? xs : xg) + (K - r);
-#pragma unroll
-    for (int it = 0; it < kMaxOwIters; ++it) {
-      const int piece = tid + it * kConsumers;
-      if (it > 0 && it * kConsumers >= npieces) break;   // uniform
-      const bool live = piece < npieces;
-      const uint32_t w4[4] = {owv[it].x, owv[it].y, owv[it].z, owv[it].w};
-      if (p.ow_layout == QEFT_OW_INTERLEAVED) {
-        // interleaved row R (local) holds rows nl and nl+4; 16 bytes = columns j0..j0+3 of both rows
-        const int per_row = r >> 2;                 // pieces per interleaved row
-        const int R = live ? piece / per_row : 0, pp = live ? piece - R * per_row : 0;
-        const int c = pp >> 3, j0 = 32 * c + 4 * (pp & 7);
-        const int nl = 8 * (R >> 2) + (R & 3);
-        for (int b = 0; b < m; ++b) {
-          float s0 = 0.f, s1 = 0.f;
-          if (live) {
-            uint2 xv = XS ? *reinterpret_cast<const uint2*>(xo + (size_t)b * xstride + j0)
-                          : ldg_nc_v2(xo + (size_t)b * xstride + j0);
-            const float2 x01 = half2_bits_to_float2(xv.x), x23 = half2_bits_to_float2(xv.y);
-            const float xf[4] = {x01.x, x01.y, x23.x, x23.y};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wv = half2_bits_to_float2(w4[j]);   // {row nl, row nl+4} at column j0+j
-              s0 = fmaf(wv.x, xf[j], s0);
-              s1 = fmaf(wv.y, xf[j], s1);
-            }
-          }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 4); s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-          if (live && (pp & 7) == 0) {
-            opart[(c * kRows + nl) * 8 + b] = s0;
-            opart[(c * kRows + nl + 4) * 8 + b] = s1;
-          }
-        }
-      } else {
-        // plain [N, r]: 16 bytes = 8 consecutive columns of one row
-        const int per_row = r >> 3;
-        const int nl = live ? piece / per_row : 0, pp = live ? piece - nl * per_row : 0;
-        const int c = pp >> 2, j0 = 8 * pp;
-        for (int b = 0; b < m; ++b) {
-          float s0 = 0.f;
-          if (live) {
-            uint4 xv = XS ? *reinterpret_cast<const uint4*>(xo + (size_t)b * xstride + j0)
-                          : ldg_nc_v4(xo + (size_t)b * xstride + j0);
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wv = half2_bits_to_float2(w4[j]);
-              const float2 xf = half2_bits_to_float2(xw[j]);
-              s0 = fmaf(wv.x, xf.x, s0);
-              s0 = fmaf(wv.y, xf.y, s0);
-            }
-          }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-          if (live && (pp & 3) == 0) opart[(c * kRows + nl) * 8 + b] = s0;
-        }
-      }
+    for (int i = tid; i < nsteps * 16; i += kThreads) {      // batch columns >= m
+      const int col = 2 * ((i >> 2) & 3) + (i & 1);
+      if (col >= m) sums_f[i] = 0.f;
     }
   }
+  __syncthreads();
 
-  // ---- main loop ------------------------------------------------------------------------------
-  float yacc[RG][4];                       // per row group: rows g, g+8 x batch columns 2t, 2t+1
+  // ---- the units of this warp -----------------------------------------------------------------------
+  // Batch column n of the B fragment only feeds output column n, so lanes of batch rows >= m simply re-read
+  // row 0 (a broadcast; their output columns are never stored): no divergence, no zero fill.
+  const int gx = g < m ? g : 0;
+  const uint32_t x_lane = smem_u32(xs) + (uint32_t)((gx * p.xstride + t * 8) * 2);
+  const uint32_t xo_lane = smem_u32(xo) + (uint32_t)((gx * r) * 2);
+  const __half* xg_lane = xg + (size_t)gx * K;
+  const uint32_t sums_lane = smem_u32(sums) + 16 * t;
+
+  // B fragments of step s: x[gx][128 s + 32 t .. +32], natural order
+  auto load_x = [&](uint32_t (&xb)[16], int s) {
+    if (XS) {
+      const uint32_t a = x_lane + (uint32_t)(s * 256);
 #pragma unroll
-  for (int q = 0; q < RG; ++q) yacc[q][0] = yacc[q][1] = yacc[q][2] = yacc[q][3] = 0.f;
-  const bool xrow_ok = g < m;
-  const int toff = (t >> 1) * 128 + (t & 1) * 16;               // this lane's 16-byte chunk inside the 256-byte step
+      for (int j = 0; j < 4; ++j) {
+        const uint4 v = lds_v4(a + 64 * j);
+        xb[4 * j + 0] = v.x; xb[4 * j + 1] = v.y; xb[4 * j + 2] = v.z; xb[4 * j + 3] = v.w;
+      }
+    } else {
+      const bool live = (4 * s + t) < nchunks;
+      const __half* xp = xg_lane + s * 128 + t * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 v = live ? ldg_nc_v4(xp + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+        xb[4 * j + 0] = v.x; xb[4 * j + 1] = v.y; xb[4 * j + 2] = v.z; xb[4 * j + 3] = v.w;
+      }
+    }
+  };
 
-  // One 128-column step of one row group: 8 words (4 of row g, 4 of row g+8) -> 8 mma in two chains.
-  // xb[4j + c] is the natural-order half2 (k = 8j + 2c, +1) of this lane's 32-column chunk, i.e. the k-pair
-  // that word c's j-th half2 multiplies.  mma (j, cc) takes k-slots (2t, 2t+1) from word 2cc and (2t+8, 2t+9)
-  // from word 2cc+1, so its B registers are the adjacent pair xb[4j + 2cc], xb[4j + 2cc + 1]; even j (low
-  // nibbles, 1024+q) accumulate in `lo`, odd j (high nibbles, 1024+16q) in `hi`.
-  auto step_math = [&](float (&ya)[4], const uint4& va, const uint4& vb, const uint32_t (&xb)[16], float mine,
-                       const float2& xs2, const float2& cs2) {
-    float lo[4], hi[4];
+  float ya[4] = {0.f, 0.f, 0.f, 0.f};      // rows ra, rb x batch columns 2t, 2t+1 of the current tile
+  auto flush = [&](int tord) {
+    float* dst = part + ((size_t)tord * kWarps + warp) * 16 * m;
+    if (2 * t < m) { dst[ra * m + 2 * t] = ya[0]; dst[rb * m + 2 * t] = ya[2]; }
+    if (2 * t + 1 < m) { dst[ra * m + 2 * t + 1] = ya[1]; dst[rb * m + 2 * t + 1] = ya[3]; }
+    ya[0] = ya[1] = ya[2] = ya[3] = 0.f;
+  };
+
+  // one 128-column int4 step: 8 words (4 of row ra, 4 of row rb) -> 8 mma in two chains.  xc[4j + w] is the
+  // natural-order half2 (k = 8j + 2w, +1) of this lane's 32-column chunk, i.e. the k-pair that word w's j-th
+  // half2 multiplies.  mma (j, cc) takes k-slots (2t, 2t+1) from word 2cc and (2t+8, 2t+9) from word 2cc+1, so
+  // its B registers are the adjacent pair xc[4j + 2cc], xc[4j + 2cc + 1]; even j (low nibbles, 1024+q)
+  // accumulate in `lo`, odd j (high nibbles, 1024+16q) in `hi`.
+  // `sp`: shared address of the step's scale rows (16 scales | 16 scaled zeros) + 2 ra.
+  auto int4_step = [&](const uint4& va, const uint4& vb, int s, uint32_t sp) {
+    uint32_t xc[16];
+    load_x(xc, s);
+    float4 sm;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sm.x), "=f"(sm.y), "=f"(sm.z), "=f"(sm.w)
+                 : "r"(sums_lane + (uint32_t)(s * 64)) : "memory");
     const uint32_t wa_[4] = {va.x, va.y, va.z, va.w};
     const uint32_t wb_[4] = {vb.x, vb.y, vb.z, vb.w};
+    float lo[4], hi[4];
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       uint32_t a0[4], a1[4], b0[4], b1[4];
@@ -381,158 +412,148 @@ gemv_w4_kernel(const GemvParams p) {
       for (int j = 0; j < 4; ++j) {
         float (&acc)[4] = (j & 1) ? hi : lo;
         if (cc == 0 && j < 2)
-          mma_m16n8k16_zero(acc, a0[j], b0[j], a1[j], b1[j], xb[4 * j + 2 * cc], xb[4 * j + 2 * cc + 1]);
+          mma_m16n8k16_zero(acc, a0[j], b0[j], a1[j], b1[j], xc[4 * j + 2 * cc], xc[4 * j + 2 * cc + 1]);
         else
-          mma_m16n8k16_f16f32(acc, a0[j], b0[j], a1[j], b1[j], xb[4 * j + 2 * cc], xb[4 * j + 2 * cc + 1]);
+          mma_m16n8k16_f16f32(acc, a0[j], b0[j], a1[j], b1[j], xc[4 * j + 2 * cc], xc[4 * j + 2 * cc + 1]);
       }
     }
-    // group epilogue.  Lane l holds scale (l < 16) / scaled zero (l >= 16) of row l % 16.
-    const float sa = __shfl_sync(0xffffffffu, mine, g), sb = __shfl_sync(0xffffffffu, mine, g + 8);
-    const float za = __shfl_sync(0xffffffffu, mine, g + 16), zb = __shfl_sync(0xffffffffu, mine, g + 24);
     // y += s * (lo + hi/16 - c) + z * X
-    ya[0] = fmaf(sa, fmaf(hi[0], 0.0625f, lo[0]) - cs2.x, fmaf(za, xs2.x, ya[0]));
-    ya[1] = fmaf(sa, fmaf(hi[1], 0.0625f, lo[1]) - cs2.y, fmaf(za, xs2.y, ya[1]));
-    ya[2] = fmaf(sb, fmaf(hi[2], 0.0625f, lo[2]) - cs2.x, fmaf(zb, xs2.x, ya[2]));
-    ya[3] = fmaf(sb, fmaf(hi[3], 0.0625f, lo[3]) - cs2.y, fmaf(zb, xs2.y, ya[3]));
+    const float sa = lds_h(sp), sbv = lds_h(sp + 8), za = lds_h(sp + 32), zb = lds_h(sp + 40);
+    ya[0] = fmaf(sa, fmaf(hi[0], 0.0625f, lo[0]) - sm.z, fmaf(za, sm.x, ya[0]));
+    ya[1] = fmaf(sa, fmaf(hi[1], 0.0625f, lo[1]) - sm.w, fmaf(za, sm.y, ya[1]));
+    ya[2] = fmaf(sbv, fmaf(hi[2], 0.0625f, lo[2]) - sm.z, fmaf(zb, sm.x, ya[2]));
+    ya[3] = fmaf(sbv, fmaf(hi[3], 0.0625f, lo[3]) - sm.w, fmaf(zb, sm.y, ya[3]));
   };
 
-  // B fragments of step s: x[g][128 s + 32 t .. +32], natural order (zero for batch rows >= m and dead chunks)
-  auto load_x = [&](uint32_t (&xb)[16], int s, bool live) {
-    if (live) {
-      const __half* xp = (XS ? xs : xg) + (size_t)g * xstride + s * 128 + t * 32;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 v = XS ? *reinterpret_cast<const uint4*>(xp + 8 * j) : ldg_nc_v4(xp + 8 * j);
-        xb[4 * j + 0] = v.x; xb[4 * j + 1] = v.y; xb[4 * j + 2] = v.z; xb[4 * j + 3] = v.w;
+  // the consume / refill protocol of one unit: wait for the oldest group, read the slot (the caller's `body`
+  // uses w0..w3 and the scale rows), then refill the slot that was read ONE unit earlier.  A lane only reads its
+  // own 16-byte chunks (no hazard); the scale rows are shared by the warp: the __syncwarp after the wait orders
+  // the previous unit's reads of them before this unit's refill, and this unit's copies before its reads.
+  int ctord = u0 / upt, csu = u0 - ctord * upt;
+  uint32_t slot = ring_u32, prev_slot = ring_u32 + (D - 1) * kSlotBytes;
+  const uint32_t ring_end = ring_u32 + D * kSlotBytes;
+  const int nfull = nchunks >> 3;            // units of a tile whose two steps are completely live
+  bool first = true;
+#pragma unroll 1
+  for (int u = u0; u < u1; ++u) {
+    const uint32_t mine = slot + lane * 16;
+    cp_async_wait<D - 2>();
+    __syncwarp();
+    if (!first) {
+      if (pu < u1) {
+        issue(prev_slot, psu);
+        ++pu;
+        if (++psu == upt) { psu = 0; ++ptord; if (pu < u1) pf_set_tile(ptord); }
       }
+      cp_async_commit();
     }
-  };
+    first = false;
+    const uint4 w0 = lds_v4(mine), w1 = lds_v4(mine + 512), w2 = lds_v4(mine + 1024), w3 = lds_v4(mine + 1536);
+    const uint32_t sp = slot + 2048 + 2 * ra;
 
-  {
-    uint32_t xb[16];
+    if (csu < nfull) {
+      // ---- two complete 128-column int4 steps, 8 mma each (the common case: no branch inside) ----
+      int4_step(w0, w1, 2 * csu, sp);
+      int4_step(w2, w3, 2 * csu + 1, sp + 64);
+    } else if (csu < nku) {
+      int4_step(w0, w1, 2 * csu, sp);
+      if (2 * csu + 1 < nsteps) int4_step(w2, w3, 2 * csu + 1, sp + 64);
+    } else {
+      // ---- outlier unit: up to 64 fp16 columns of the tile's 16 rows, 4 mma ----
+      const int c0 = 64 * (csu - nku);
+      if (inter) {
+        const uint4 wv[4] = {w0, w1, w2, w3};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) xb[j] = 0u;
-    // this lane's bytes inside a stage: rows g (qweight row g/4) and g+8 (two qweight rows further) of row group q
-    const uint32_t offA = (uint32_t)((g >> 2) * kRowBytes + warp * kStepBytes + (g & 3) * 32 + toff);
-    // scale (lanes 0-15) / scaled zero (lanes 16-31) of row lane % 16
-    const __half* my_sc = sctab + (lane >> 4) * 16 + (lane & 15);
-    int st = 0;
-    uint32_t parity = 0;
-    for (int s = warp; s < nfull; s += WARPS) {
-      load_x(xb, s, xrow_ok);
-      const int grp = G128 ? s : (p.g128 == 0 ? 0 : s / p.g128);
-      float mine[RG];
+        for (int j = 0; j < 4; ++j) {
+          if (c0 + 16 * j < r) {                  // uniform
+            const uint4 u4 = wv[j];               // {ra, rb} at columns c0 + 16 j + 4t .. + 3
+            uint2 xv;
+            if (XS) xv = lds_v2(xo_lane + (uint32_t)((c0 + 16 * j + 4 * t) * 2));
+            else xv = ldg_nc_v2(xg_lane + K - r + c0 + 16 * j + 4 * t);
+            mma_m16n8k16_f16f32(ya, prmt(u4.x, u4.y, 0x5410), prmt(u4.x, u4.y, 0x7632), prmt(u4.z, u4.w, 0x5410),
+                                prmt(u4.z, u4.w, 0x7632), xv.x, xv.y);
+          }
+        }
+      } else {
 #pragma unroll
-      for (int q = 0; q < RG; ++q) mine[q] = __half2float(my_sc[(grp * RG + q) * 32]);
-      const float2 xs2 = *reinterpret_cast<const float2*>(xsum + s * 8 + 2 * t);
-      const float2 cs2 = *reinterpret_cast<const float2*>(csum + s * 8 + 2 * t);
-      mbar_wait(full_u32 + 8 * st, parity);
-      const uint8_t* sb = ring + (size_t)st * kStageBytes;
-      uint4 va[RG], vb[RG];
-#pragma unroll
-      for (int q = 0; q < RG; ++q) {
-        // dead rows (beyond N) read whatever the ring holds: finite garbage that is never stored
-        va[q] = *reinterpret_cast<const uint4*>(sb + offA + q * 4 * kRowBytes);
-        vb[q] = *reinterpret_cast<const uint4*>(sb + offA + q * 4 * kRowBytes + 2 * kRowBytes);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_u32 + 8 * st);        // the stage's bytes of this warp are in registers
-#pragma unroll
-      for (int q = 0; q < RG; ++q) step_math(yacc[q], va[q], vb[q], xb, mine[q], xs2, cs2);
-      if (++st == stages) { st = 0; parity ^= 1u; }
-    }
-    // partial last step (K - r not a multiple of 128): chunks beyond K - r are dead
-    if (nfull < nsteps && warp == (nfull % WARPS)) {
-      const int sl = nfull;
-      const bool live = (4 * sl + t) < nchunks;
-      const int grp = G128 ? sl : (p.g128 == 0 ? 0 : sl / p.g128);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) xb[j] = 0u;
-      load_x(xb, sl, xrow_ok && live);
-      const float2 xs2 = *reinterpret_cast<const float2*>(xsum + sl * 8 + 2 * t);
-      const float2 cs2 = *reinterpret_cast<const float2*>(csum + sl * 8 + 2 * t);
-#pragma unroll
-      for (int q = 0; q < RG; ++q) {
-        // a dead lane (or a dead row) re-reads chunk 0 of a live row: always mapped, multiplied by x = 0 / never stored
-        const int qa = min((n0 >> 2) + 4 * q + (g >> 2), (N >> 2) - 1);
-        const int qb = min((n0 >> 2) + 4 * q + 2 + (g >> 2), (N >> 2) - 1);
-        const size_t inrow = (size_t)(g & 3) * 32 + (size_t)sl * 256 + (live ? toff : 0);
-        const uint4 va = ldg_stream_v4(P.qw + (size_t)qa * (size_t)(2 * K) + inrow);
-        const uint4 vb = ldg_stream_v4(P.qw + (size_t)qb * (size_t)(2 * K) + inrow);
-        const float mine = __half2float(my_sc[(grp * RG + q) * 32]);
-        step_math(yacc[q], va, vb, xb, mine, xs2, cs2);
+        for (int si = 0; si < 2; ++si) {
+          if (c0 + 32 * si < r) {                 // uniform
+            const uint4 ua = si ? w2 : w0, ub = si ? w3 : w1;   // rows ra / rb, columns c0 + 32 si + 8t .. + 7
+            uint4 xv;
+            if (XS) xv = lds_v4(xo_lane + (uint32_t)((c0 + 32 * si + 8 * t) * 2));
+            else xv = ldg_nc_v4(xg_lane + K - r + c0 + 32 * si + 8 * t);
+            mma_m16n8k16_f16f32(ya, ua.x, ub.x, ua.y, ub.y, xv.x, xv.y);
+            mma_m16n8k16_f16f32(ya, ua.z, ub.z, ua.w, ub.w, xv.z, xv.w);
+          }
+        }
       }
     }
+    if (++csu == upt) { flush(ctord); csu = 0; ++ctord; }
+    prev_slot = slot;
+    slot += kSlotBytes;
+    if (slot == ring_end) slot = ring_u32;
   }
+  if (csu != 0) flush(ctord);
+  cp_async_wait<0>();
 
-  // ---- meet the k-split partial sums ----------------------------------------------------------------
-  {
-    float* my = red + warp * kRows * 8;
+  // ---- add the warps' slices in a fixed order, round, store the rows this CTA owns -------------------------
+  __syncthreads();
+  for (int i = tid; i < ntiles * 16 * m; i += kThreads) {
+    const int b = i % m, rr = (i / m) & 15, tord = i / (16 * m);
+    int sg = 0;
 #pragma unroll
-    for (int q = 0; q < RG; ++q) {
-      *reinterpret_cast<float2*>(my + (16 * q + g) * 8 + 2 * t) = make_float2(yacc[q][0], yacc[q][1]);
-      *reinterpret_cast<float2*>(my + (16 * q + g + 8) * 8 + 2 * t) = make_float2(yacc[q][2], yacc[q][3]);
-    }
-  }
-  named_bar_sync(1, kConsumers);
-  for (int i = tid; i < kRows * m; i += kConsumers) {
-    const int b = i / kRows, nl = i - b * kRows;
-    if (n0 + nl < N) {
+    for (int j = 1; j < QEFT_GEMV_MAX_PARTS; ++j)
+      if (j < nseg && tord >= segs[j].cum) sg = j;
+    const Seg S = segs[sg];
+    const int row = 16 * (S.t0 + tord - S.cum) + rr;
+    const int q = row >> 2;
+    if (q >= S.pa && q < S.pb) {
+      const GemvPart& P = p.part[S.part];
+      const float* src = part + (size_t)tord * kWarps * 16 * m + rr * m + b;
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) acc += red[(w * kRows + nl) * 8 + b];
-      for (int c = 0; c < (r >> 5); ++c) acc += opart[(c * kRows + nl) * 8 + b];
-      if (P.bias) acc += __half2float(P.bias[n0 + nl]);
-      P.y[(size_t)b * N + n0 + nl] = __float2half_rn(acc);
+      for (int w = 0; w < kWarps; ++w) acc += src[w * 16 * m];
+      if (P.bias) acc += __half2float(P.bias[row]);
+      P.y[(size_t)b * P.N + row] = __float2half_rn(acc);
     }
   }
 }
 
 // ----------------------------------------------------------------------------------------------------
-constexpr int kGemvWarps = 8;
-constexpr int kGemvMinBlocks = 2;
-constexpr int kGemvStageCap = 4;                // rounds in flight per CTA: enough to cover HBM latency with two CTAs per
-                                                // SM, small enough that the dependent x fetch does not queue behind them
-constexpr size_t kStageXMaxBytes = 72 * 1024;   // stage x in shared memory when it is at most this big
-constexpr size_t kSmemPerSm = 226 * 1024;
-constexpr int kNumSms = 148;
+constexpr size_t kStageXMaxBytes = 64 * 1024;   // stage x in shared memory when it is at most this big
+constexpr size_t kSmemPerSm = 227 * 1024;
+constexpr size_t kSmemCtaOverhead = 1024 + 256; // per-CTA reservation + static shared
+constexpr size_t kPartMaxBytes = 24 * 1024;     // partial-sum slices per CTA; larger launches are split by rows
 
-static size_t gemv_fixed_smem(int rg, int m, int K, int r, int ngroups, bool xs) {
-  const int nsteps = cdiv(K - r, 128);
-  const int rows = rg * 16;
-  size_t b = (2 * kMaxStages + 2) * sizeof(uint64_t) +
-             sizeof(float) * ((size_t)kGemvWarps * rows * 8 + 2 * (size_t)nsteps * 8 + (size_t)(r >> 5) * rows * 8) +
-             sizeof(__half) * (size_t)ngroups * rg * 32;
-  if (xs) b += sizeof(__half) * (size_t)m * (size_t)(K + 8);
-  return (b + 127) & ~(size_t)127;
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int RG, bool XS, bool G128>
-static int launch_gemv(GemvParams& prm, int total_ctas, unsigned flags, cudaStream_t stream) {
-  auto kern = gemv_w4_kernel<kGemvWarps, RG, XS, G128, kGemvMinBlocks>;
-  constexpr size_t stage_bytes = (size_t)RG * 4 * kGemvWarps * kStepBytes;
-  const size_t fixed = gemv_fixed_smem(RG, prm.m, prm.K, prm.r, prm.ngroups, XS);
-  prm.rounds = cdiv(prm.nfull, kGemvWarps);
-  // CTAs per SM: 4 (so that two consecutive launches are co-resident and the next layer's weights stream in
-  // under programmatic dependent launch while this one computes), else 2, else 1 -- whatever leaves the ring
-  // at least four stages
-  size_t budget = kSmemPerSm / 2;
-  if (fixed + 3 * stage_bytes > budget) budget = kSmemPerSm;
-  if (fixed + stage_bytes > budget) return QEFT_E_UNSUPPORTED;
-  int stages = (int)((budget - fixed) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > kGemvStageCap) stages = kGemvStageCap;
-  if (stages > prm.rounds) stages = prm.rounds;
-  if (stages < 1) stages = 1;
-  prm.stages = stages;
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <int D, bool XS>
+static int launch_one(const GemvParams& prm, int grid, size_t smem, unsigned flags, cudaStream_t stream) {
+  auto kern = gemv_w4_kernel<D, XS>;
+  static bool attr_set[64] = {};    // per instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerSm - 1024));
     if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)total_ctas);
-  cfg.blockDim = dim3((kGemvWarps + 1) * 32);
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -540,18 +561,55 @@ static int launch_gemv(GemvParams& prm, int total_ctas, unsigned flags, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (flags & QEFT_F_PDL) ? 1 : 0;
-  prm.pdl = (flags & QEFT_F_PDL) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
   if (e != cudaSuccess) return (int)e;
   count_launch();
   return QEFT_OK;
 }
 
-template <int RG>
-static int dispatch_gemv(GemvParams& prm, int ctas, bool stage, unsigned flags, cudaStream_t st) {
-  if (prm.g128 == 1)
-    return stage ? launch_gemv<RG, true, true>(prm, ctas, flags, st) : launch_gemv<RG, false, true>(prm, ctas, flags, st);
-  return stage ? launch_gemv<RG, true, false>(prm, ctas, flags, st) : launch_gemv<RG, false, false>(prm, ctas, flags, st);
+template <bool XS>
+static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_t stream) {
+  static const int depth_env = env_int("QEFT_GEMV_DEPTH", 0);
+  static const int cps_env = env_int("QEFT_GEMV_CTAS_PER_SM", 1);
+  const int m = prm.m;
+  const size_t xbytes = XS ? sizeof(__half) * (size_t)m * (size_t)(prm.xstride + prm.r) : 0;
+  const size_t sums = sizeof(float) * 16 * (size_t)prm.nsteps;
+  const int sms = num_sms() * (cps_env > 0 ? cps_env : 1);
+  // rows per launch: the partial-sum slices of a CTA must fit kPartMaxBytes
+  const size_t tile_part = sizeof(float) * kWarps * 16 * (size_t)m;
+  int tiles_fit = (int)(kPartMaxBytes / tile_part);
+  if (tiles_fit < 3) tiles_fit = 3;
+  const int q_per_cta_max = 4 * (tiles_fit - 2 * prm.nparts > 1 ? tiles_fit - 2 * prm.nparts : 1);
+  for (int q_lo = 0; q_lo < total_q;) {
+    int q_hi = total_q;
+    int grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
+    if ((long)grid * q_per_cta_max < (long)(q_hi - q_lo)) q_hi = q_lo + grid * q_per_cta_max;
+    prm.q_lo = q_lo; prm.q_hi = q_hi;
+    grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
+    const int qmax = cdiv(q_hi - q_lo, grid);
+    prm.max_tiles = cdiv(qmax, 4) + 2 * prm.nparts;
+    const size_t fixed = (size_t)prm.max_tiles * tile_part + sums + xbytes + 128;
+    // two CTAs per SM (this launch's and, under programmatic dependent launch, the next one's) when the ring
+    // still gets at least 4 units per warp; else the whole SM
+    size_t budget = kSmemPerSm / 2 - kSmemCtaOverhead;
+    if (fixed + (size_t)kWarps * 4 * kSlotBytes > budget) budget = kSmemPerSm - kSmemCtaOverhead;
+    if (fixed + (size_t)kWarps * 2 * kSlotBytes > budget) return QEFT_E_UNSUPPORTED;
+    int depth = (int)((budget - fixed) / ((size_t)kWarps * kSlotBytes));
+    if (depth_env > 0 && depth > depth_env) depth = depth_env;
+    int st;
+#define QEFT_GEMV_LAUNCH(DD) st = launch_one<DD, XS>(prm, grid, fixed + (size_t)kWarps * DD * kSlotBytes, flags, stream)
+    if (depth >= 10) QEFT_GEMV_LAUNCH(10);
+    else if (depth >= 8) QEFT_GEMV_LAUNCH(8);
+    else if (depth >= 6) QEFT_GEMV_LAUNCH(6);
+    else if (depth >= 5) QEFT_GEMV_LAUNCH(5);
+    else if (depth >= 4) QEFT_GEMV_LAUNCH(4);
+    else if (depth >= 3) QEFT_GEMV_LAUNCH(3);
+    else QEFT_GEMV_LAUNCH(2);
+#undef QEFT_GEMV_LAUNCH
+    if (st != QEFT_OK) return st;
+    q_lo = q_hi;
+  }
+  return QEFT_OK;
 }
 
 }  // namespace qeft
@@ -569,10 +627,9 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
   if (r < 0 || r % 32 != 0 || r >= K) return QEFT_E_SHAPE;
   if (r > 0 && ow_layout != QEFT_OW_PLAIN && ow_layout != QEFT_OW_INTERLEAVED) return QEFT_E_DTYPE;
   if (r == 0) ow_layout = QEFT_OW_NONE;
-  if (r > 256) return QEFT_E_UNSUPPORTED;   // TODO(next): loop the outlier pieces
   if (!check_align16(x)) return QEFT_E_ALIGN;
   GemvParams prm = {};
-  long total_rows = 0;
+  int total_q = 0;
   for (int i = 0; i < nparts; ++i) {
     const qeft_gemv_part_t& q = parts[i];
     if (!q.qweight || !q.scales || !q.scaled_zeros || !q.y) return QEFT_E_NULL;
@@ -581,13 +638,6 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
     if (!check_align16(q.qweight) || !check_align16(q.scales) || !check_align16(q.scaled_zeros) ||
         (r > 0 && !check_align16(q.oweight)))
       return QEFT_E_ALIGN;
-    total_rows += q.N;
-  }
-  // two 16-row groups per CTA once that still gives every SM at least two CTAs (halves the per-CTA x work)
-  const int rg = (total_rows >= 2L * kNumSms * 32) ? 2 : 1;
-  int ctas = 0;
-  for (int i = 0; i < nparts; ++i) {
-    const qeft_gemv_part_t& q = parts[i];
     GemvPart& d = prm.part[i];
     d.qw = static_cast<const uint8_t*>(q.qweight);
     d.scales = static_cast<const __half*>(q.scales);
@@ -596,8 +646,8 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
     d.bias = static_cast<const __half*>(q.bias);
     d.y = static_cast<__half*>(q.y);
     d.N = q.N;
-    d.cta_begin = ctas;
-    ctas += cdiv(q.N, 16 * rg);
+    d.q_begin = total_q;
+    total_q += q.N / 4;
   }
   prm.nparts = nparts;
   prm.x = static_cast<const __half*>(x);
@@ -606,13 +656,13 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
   prm.g128 = (G == K) ? 0 : G / 128;
   prm.ow_layout = ow_layout;
   prm.nsteps = cdiv(K - r, 128);
-  prm.nfull = (K - r) / 128;
   prm.nchunks = (K - r) / 32;
-  prm.xstride = K + 8;
-  prm.ngroups = (prm.g128 == 0) ? 1 : cdiv(prm.nsteps, prm.g128);
+  prm.nku = cdiv(prm.nsteps, 2);
+  prm.nou = cdiv(r, 64);
+  prm.xstride = 128 * prm.nsteps + 32;   // the int4 steps' columns (dead columns of the last step staged as zeros)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool stage = x_gather != nullptr || (size_t)m * (size_t)(K + 8) * 2 <= kStageXMaxBytes;
-  return rg == 2 ? dispatch_gemv<2>(prm, ctas, stage, flags, st) : dispatch_gemv<1>(prm, ctas, stage, flags, st);
+  const bool stage = x_gather != nullptr || (size_t)m * (size_t)(K + 136) * 2 <= kStageXMaxBytes;
+  return stage ? launch_gemv<true>(prm, total_q, flags, st) : launch_gemv<false>(prm, total_q, flags, st);
 }
 
 extern "C" int qeft_gemv_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
