@@ -570,11 +570,15 @@ static int launch_one(const GemvParams& prm, int grid, size_t smem, unsigned fla
 template <bool XS>
 static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_t stream) {
   static const int depth_env = env_int("QEFT_GEMV_DEPTH", 0);
-  static const int cps_env = env_int("QEFT_GEMV_CTAS_PER_SM", 1);
+  static const int cps_env = env_int("QEFT_GEMV_CTAS_PER_SM", 0);
   const int m = prm.m;
   const size_t xbytes = XS ? sizeof(__half) * (size_t)m * (size_t)(prm.xstride + prm.r) : 0;
   const size_t sums = sizeof(float) * 16 * (size_t)prm.nsteps;
-  const int sms = num_sms() * (cps_env > 0 ? cps_env : 1);
+  // the kernel is bound by instruction issue, not by bytes in flight: wide launches run two CTAs per SM (16 warps)
+  // once every CTA still gets at least 8 qweight rows; narrow ones keep one CTA per SM so that the next launch's
+  // CTA can be co-resident under programmatic dependent launch
+  const int cps = cps_env > 0 ? cps_env : (total_q >= 2 * 8 * num_sms() ? 2 : 1);
+  const int sms = num_sms() * cps;
   // rows per launch: the partial-sum slices of a CTA must fit kPartMaxBytes
   const size_t tile_part = sizeof(float) * kWarps * 16 * (size_t)m;
   int tiles_fit = (int)(kPartMaxBytes / tile_part);

@@ -1,0 +1,101 @@
+"""Parity of the tcgen05 prefill / fine-tune GEMM (through the C ABI) against the CPU oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3   # north_star: max relative error 1e-3 for the fp16 path (vs the reference dequant + matmul)
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-6))
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def run_gemm(L, x, bias=None, with_outliers=True):
+    from qeft_b200 import qeft_cuda
+    ow = dev(L["oweight"]) if (with_outliers and L["r"] > 0) else None
+    y = qeft_cuda.gemm_w4(dev(x), dev(L["qweight"]), dev(L["scales"]), dev(L["scaled_zeros"]), ow,
+                          None if bias is None else dev(bias), group_size=L["G"], pdl=False)
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+@pytest.mark.parametrize("M,N,K,r,G", [
+    (8, 128, 128, 0, 128),          # smallest legal: one k-block pair, one 128-feature block
+    (128, 256, 256, 64, 128),       # both feature blocks, one outlier k-block
+    (77, 128, 512, 128, 128),       # ragged token count (TMA zero-fills, stores are masked)
+    (300, 384, 1024, 128, 128),     # N % 256 == 128: last tile has one feature block; three token tiles
+    (256, 256, 512, 0, 512),        # per-channel scales (G == K)
+    (130, 512, 768, 192, 256),      # G = 256, r = 192
+])
+def test_gemm_matches_oracle(M, N, K, r, G):
+    L = oracle.synth_layer(N, K, r=r, G=G, seed=M + N + K + r, bias=True)
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    want = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L.get("oweight"), L["bias"], group_size=G)
+    got = run_gemm(L, x, bias=L["bias"])
+    assert got.shape == (M, N) and got.dtype == np.float16
+    assert rel_err(got, want) <= REL_TOL, rel_err(got, want)
+
+
+def test_gemm_reference_signature_uses_all_int4_columns():
+    """`gemm_4bit` of the reference has no outlier term: every int4 column counts (gemm_cuda.cu:929-1033)."""
+    from qeft_b200 import qeft_cuda
+    L = oracle.synth_layer(256, 512, r=128, seed=9)
+    x = np.random.default_rng(9).standard_normal((64, 512)).astype(np.float16)
+    W = oracle.dequant_weight(L["qweight"], L["scales"], L["scaled_zeros"]).astype(np.float64)
+    want = (x.astype(np.float64) @ W.T).astype(np.float16)
+    got = qeft_cuda.gemm_4bit(dev(x), dev(L["qweight"]), dev(L["scales"]), dev(L["scaled_zeros"]))
+    torch.cuda.synchronize()
+    assert rel_err(got.cpu().numpy(), want) <= REL_TOL
+
+
+def test_gemm_equals_gemv_on_the_same_rows():
+    """Prefill and decode agree: the GEMM's rows match the GEMV of the same activations within tolerance."""
+    from qeft_b200 import _lib, qeft_cuda
+    N, K, r = 512, 1024, 128
+    L = oracle.synth_layer(N, K, r=r, seed=21, bias=True)
+    x = np.random.default_rng(21).standard_normal((16, K)).astype(np.float16)
+    yg = run_gemm(L, x, bias=L["bias"])
+    xd = dev(x[:4])
+    yv = qeft_cuda.gemv_w4(xd, dev(L["qweight"]), dev(L["scales"]), dev(L["scaled_zeros"]), dev(L["oweight_interleaved"]),
+                           4, N, K, 128, ow_layout=_lib.OW_INTERLEAVED, bias=dev(L["bias"]))
+    torch.cuda.synchronize()
+    assert rel_err(yg[:4], yv.cpu().numpy()) <= REL_TOL
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (11008, 4096), (4096, 11008)])
+def test_gemm_llama7b_shapes_m2048_properties(shape):
+    """Full size (BASELINE.json config 3): checked by linearity against sampled oracle rows/columns."""
+    from qeft_b200 import qeft_cuda
+    from qeft_b200.synth import synth_tensors, to_numpy_layer
+    N, K = shape
+    M = 2048
+    t = synth_tensors(N, K, seed=3)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.randn((M, K), device="cuda", generator=g).half()
+    y = qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, pdl=False)
+    torch.cuda.synchronize()
+    L = to_numpy_layer(t, N, K, 128, 128)
+    rows = np.array([0, 1, 127, 128, 1000, 2047])
+    want = oracle.forward(x[rows].cpu().numpy(), L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"])
+    assert rel_err(y[rows].cpu().numpy(), want) <= REL_TOL
+    # linearity in x: gemm(2 x) == 2 gemm(x) exactly in fp16 (power-of-two scaling commutes with every rounding
+    # of a NORMAL fp16 result; subnormal results round on an absolute grid and are excluded)
+    y2 = qeft_cuda.gemm_w4((x * 2).half(), t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, pdl=False)
+    torch.cuda.synchronize()
+    normal = y.float().abs() >= 2.0 ** -13
+    assert torch.equal(y2[normal], (y.float() * 2).half()[normal])
+    # and the kernel is deterministic
+    y3 = qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, pdl=False)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y3)
