@@ -1,0 +1,412 @@
+// Backward of the packed QEFT QuantLinear on tcgen05 tensor cores (sm_100a).
+//
+//   dx[M, K]  = dy[M, N] . Wdense[N, K]          (contraction over the N output features)
+//   dow[N, r] = dy[M, N]^T . x[M, K-r : K]       (gradient of the trainable fp16 outlier columns, fp32)
+//
+// The math BASELINE.json defines for QuantMatMulQEFT.backward; the reference's own backward
+// (qeft/qlinear.py:28-44) calls the forward GEMM on dy and is not usable.
+//
+// dX (DESIGN.md "Backward"): the contraction index is the ROW of the packed weight, so the dequantised tile is
+// used as an MN-major B operand: a 16-byte packed chunk is 32 consecutive k of one row n, i.e. 64 contiguous
+// bytes of fp16 in the B tile's row n -- exactly the MN-major SWIZZLE_128B canonical layout (128-byte rows of
+// 64 consecutive k).  512 dequant threads each convert one chunk per k-block (lop3 magic number + HFMA2, the
+// same arithmetic as the forward) and store it with four 16-byte swizzled stores; dy tiles arrive by TMA
+// (K-major A operand).  One CTA computes 256 tokens x 256 input features: two fp32 accumulators of 256 TMEM
+// columns (all of tensor memory), so one dequantised tile feeds both token blocks.  The outlier columns
+// K-r..K-1 take their B rows from oweight instead of the (dead) int4 columns.
+//
+// dOW: a plain dense GEMM, both operands MN-major straight from their row-major tensors by TMA
+// (A = dy[tok, n0 .. n0+127], B = x_out[tok, 0 .. r-1]), fp32 accumulate, fp32 store / accumulate.
+#include "tc_common.cuh"
+
+namespace qeft {
+
+// ======================================================================================================
+// dX
+// ======================================================================================================
+constexpr int kDxBK = 64;                 // contraction (n) per k-block
+constexpr int kDxBF = 256;                // input features (k) per CTA = UMMA N
+constexpr int kDxTB = 2;                  // 128-token blocks per CTA
+constexpr int kDxStages = 3;
+constexpr int kDxABytes = kDxTB * 128 * kDxBK * 2;     // dy tiles of a stage (32 KB)
+constexpr int kDxBBytes = kDxBK * kDxBF * 2;           // dequantised weight tile of a stage (32 KB)
+constexpr int kDxStageBytes = kDxABytes + kDxBBytes;
+constexpr int kDxDequantWarps = 16;
+constexpr int kDxThreads = (4 + kDxDequantWarps) * 32;
+
+struct DxParams {
+  const uint8_t* qw;
+  const __half* scales;
+  const __half* szeros;
+  const __half* ow;        // [N, r] or null
+  __half* dx;              // [M, K]
+  int M, N, K, r, G;
+};
+
+__global__ void __launch_bounds__(kDxThreads, 1)
+gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kDxStages + 1];
+  __shared__ uint32_t s_tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t st0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_addr(bars);
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 8 * (kDxStages + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * kDxStages);
+
+  const int tok0 = blockIdx.x * (128 * kDxTB);
+  const int kf0 = blockIdx.y * kDxBF;
+  const int nkb = p.N / kDxBK;
+  const int ntb = (p.M - tok0) > 128 ? 2 : 1;       // token blocks with at least one live token
+
+  if (tid == 0) {
+    for (int s = 0; s < kDxStages; ++s) { mbar_init(full(s), 1 + kDxDequantWarps); mbar_init(empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem_base)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem_base;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ================= TMA producer: dy tiles (A operand, K-major) =================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&dymap) : "memory");
+      pdl_wait();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kDxStages, use = kb / kDxStages;
+        if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
+        mbar_expect_tx(full(s), (uint32_t)(ntb * 128 * kDxBK * 2));
+        for (int tb = 0; tb < ntb; ++tb)
+          tma_load_2d(st0 + s * kDxStageBytes + tb * (128 * kDxBK * 2), &dymap, kb * kDxBK, tok0 + 128 * tb, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kDxBF, false, true);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kDxStages;
+        mbar_wait(full(s), (uint32_t)((kb / kDxStages) & 1));
+        tc_fence_after();
+        const uint32_t a0 = st0 + s * kDxStageBytes, b0 = a0 + kDxABytes;
+#pragma unroll
+        for (int k16 = 0; k16 < kDxBK / 16; ++k16) {
+          // B: rows = n (k index of the MMA), 16 rows further per UMMA_K; 64-feature chunks 8 KB apart
+          const uint64_t bdesc = make_sw128_desc(b0 + k16 * 16 * 128, kDxBK * 128, 1024);
+          for (int tb = 0; tb < ntb; ++tb) {
+            const uint64_t adesc = make_sw128_desc(a0 + tb * (128 * kDxBK * 2) + k16 * 32, 16, 1024);
+            umma_ss_f16(tmem + 256 * tb, adesc, bdesc, idesc, (uint32_t)((kb | k16) != 0));
+          }
+        }
+        tc_commit(empty(s));
+      }
+      tc_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    // ================= dequant warps: one packed chunk (row n, 32 features) per thread and k-block =================
+    const int dt = tid - 128;                 // 0..511
+    const int nl = dt >> 3, kc = dt & 7;      // row within the k-block, 32-feature chunk within the tile
+    const int kf = kf0 + 32 * kc;             // first feature of this thread's chunk
+    const bool live = kf < p.K;
+    const bool outl = live && p.ow != nullptr && kf >= p.K - p.r;
+    const int grp = live ? kf / p.G : 0;
+    // packed byte offset inside a qweight row: 64-column tile, then (sub-row, half)
+    const size_t in_row = (size_t)(kf >> 6) * 128 + (size_t)(((kf >> 5) & 1) * 16);
+    // destination: 64-feature chunk kc/2 (8 KB apart), row nl, 16-byte chunks (kc%2)*4 + i, XOR-swizzled with nl%8
+    const uint32_t dst_row = (uint32_t)((kc >> 1) * (kDxBK * 128) + nl * 128);
+    const int sw = nl & 7;
+    auto load_q = [&](int kb, uint4& q, unsigned short& sh, unsigned short& zh) {
+      const int n = kb * kDxBK + nl;
+      if (outl) return;
+      q = ldg_nc_v4(p.qw + (size_t)(n >> 2) * (size_t)(2 * p.K) + (size_t)((n & 3) * 32) + in_row);
+      sh = ldg_nc_u16(p.scales + (size_t)grp * p.N + n);
+      zh = ldg_nc_u16(p.szeros + (size_t)grp * p.N + n);
+    };
+    uint4 q = make_uint4(0, 0, 0, 0), qn = q;
+    unsigned short sh = 0, zh = 0, shn = 0, zhn = 0;
+    if (live) load_q(0, q, sh, zh);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kDxStages, use = kb / kDxStages;
+      if (live && kb + 1 < nkb) load_q(kb + 1, qn, shn, zhn);
+      uint32_t v[16];
+      if (!live) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      } else if (outl) {
+        const __half* src = p.ow + (size_t)(kb * kDxBK + nl) * p.r + (kf - (p.K - p.r));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 t4 = ldg_nc_v4(src + 8 * i);
+          v[4 * i + 0] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+        }
+      } else {
+        const uint32_t s2 = (uint32_t)sh | ((uint32_t)sh << 16), z2 = (uint32_t)zh | ((uint32_t)zh << 16);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hq[4];
+          unpack_word_to_half2(w[c], hq);                        // pairs k = 2 c + 8 j (+1), exact 0..15
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[c + 4 * j] = hfma2_u32(hq[j], s2, z2);     // w = fma(q, s, sz)
+        }
+      }
+      if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
+      const uint32_t base = st0 + s * kDxStageBytes + kDxABytes + dst_row;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a = base + (uint32_t)(((((kc & 1) << 2) + i) ^ sw) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]),
+                     "r"(v[4 * i + 3]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full(s));
+      q = qn; sh = shn; zh = zhn;
+    }
+
+    // ---- epilogue: lanes = tokens, columns = features -> fp16, 16-byte stores ----
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int dw = warp - 4, quad = dw & 3, tb = (dw >> 2) & 1, fh = dw >> 3;
+    const int tok = tok0 + 128 * tb + 32 * quad + lane;
+    if (tb < ntb) {
+      const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(256 * tb + 128 * fh);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(lane_taddr + 32 * c, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int f0 = kf0 + 128 * fh + 32 * c;
+        if (tok < p.M && f0 < p.K) {
+          __half* dst = p.dx + (size_t)tok * p.K + f0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            __half2 h;
+            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 0]), __uint_as_float(acc[8 * i + 1])); o.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])); o.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])); o.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])); o.w = *reinterpret_cast<uint32_t*>(&h);
+            *reinterpret_cast<uint4*>(dst + 8 * i) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+// ======================================================================================================
+// dOW
+// ======================================================================================================
+constexpr int kDwBK = 64;                 // tokens per k-block
+constexpr int kDwStages = 4;
+constexpr int kDwThreads = 192;           // warp 0 TMA, warp 1 MMA (+ TMEM alloc), warps 2-5 epilogue
+
+struct DowParams {
+  float* dow;              // [N, r]
+  int M, N, r, accumulate;
+};
+
+// one CTA: 128 output features n0..n0+127 x all r (<= 256) outlier columns, contraction over all M tokens
+__global__ void __launch_bounds__(kDwThreads, 1)
+dow_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xomap, const DowParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kDwStages + 1];
+  __shared__ uint32_t s_tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t st0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_addr(bars);
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 8 * (kDwStages + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * kDwStages);
+  const int n0 = blockIdx.x * 128;
+  const int nkb = cdiv(p.M, kDwBK);
+  const int rchunks = p.r / 64;                                 // 64-column chunks of the outlier block
+  const uint32_t a_bytes = 2 * kDwBK * 128;                     // 128 features = two 64-wide chunks of 64 token rows
+  const uint32_t stage_bytes = a_bytes + (uint32_t)rchunks * kDwBK * 128;
+
+  if (tid == 0) {
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem_base)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem_base;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kDwStages, use = kb / kDwStages;
+        if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
+        mbar_expect_tx(full(s), stage_bytes);
+        const uint32_t base = st0 + s * stage_bytes;
+        // rows = tokens (the MMA's k index), 128-byte rows of 64 consecutive features: MN-major tiles
+        tma_load_2d(base, &dymap, n0, kb * kDwBK, full(s));
+        tma_load_2d(base + kDwBK * 128, &dymap, n0 + 64, kb * kDwBK, full(s));
+        for (int c = 0; c < rchunks; ++c) tma_load_2d(base + a_bytes + c * (kDwBK * 128), &xomap, 64 * c, kb * kDwBK, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.r, true, true);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kDwStages;
+        mbar_wait(full(s), (uint32_t)((kb / kDwStages) & 1));
+        tc_fence_after();
+        const uint32_t a0 = st0 + s * stage_bytes, b0 = a0 + a_bytes;
+#pragma unroll
+        for (int k16 = 0; k16 < kDwBK / 16; ++k16) {
+          const uint64_t adesc = make_sw128_desc(a0 + k16 * 16 * 128, kDwBK * 128, 1024);
+          const uint64_t bdesc = make_sw128_desc(b0 + k16 * 16 * 128, kDwBK * 128, 1024);
+          umma_ss_f16(tmem, adesc, bdesc, idesc, (uint32_t)((kb | k16) != 0));
+        }
+        tc_commit(empty(s));
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // epilogue: lane = feature n, columns = outlier column j
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int quad = warp & 3;                    // warps 2..5 -> quadrants 2, 3, 0, 1
+    const int n = n0 + 32 * quad + lane;
+    const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16);
+    for (int c = 0; c < p.r / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld32(lane_taddr + 32 * c, acc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* dst = p.dow + (size_t)n * p.r + 32 * c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 o = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                               __uint_as_float(acc[4 * i + 3]));
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(dst + 4 * i);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(dst + 4 * i) = o;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+  }
+}
+
+template <typename Kern>
+static int set_smem_once(Kern kern, size_t smem, bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  return QEFT_OK;
+}
+
+}  // namespace qeft
+
+using namespace qeft;
+
+extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* scales, const void* scaled_zeros,
+                               const void* oweight, void* dx, int M, int N, int K, int r, int G, int dtype,
+                               unsigned flags, qeft_stream_t stream) {
+  if (!dy || !qweight || !scales || !scaled_zeros || !dx) return QEFT_E_NULL;
+  if (dtype != QEFT_DT_F16) return dtype == QEFT_DT_BF16 ? QEFT_E_UNSUPPORTED : QEFT_E_DTYPE;
+  if (G == -1) G = K;
+  if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 64 != 0 || G <= 0 || G % 64 != 0 || K % G != 0) return QEFT_E_SHAPE;
+  if (r < 0 || r % 64 != 0 || r >= K) return QEFT_E_SHAPE;
+  if (r > 0 && !oweight) return QEFT_E_NULL;
+  if (!check_align16(dy) || !check_align16(qweight) || !check_align16(dx) || (r > 0 && !check_align16(oweight))) return QEFT_E_ALIGN;
+  CUtensorMap dymap;
+  int st = make_tmap_f16_2d(&dymap, dy, (uint64_t)M, (uint64_t)N, 128);
+  if (st != QEFT_OK) return st;
+  DxParams prm;
+  prm.qw = static_cast<const uint8_t*>(qweight);
+  prm.scales = static_cast<const __half*>(scales);
+  prm.szeros = static_cast<const __half*>(scaled_zeros);
+  prm.ow = r > 0 ? static_cast<const __half*>(oweight) : nullptr;
+  prm.dx = static_cast<__half*>(dx);
+  prm.M = M; prm.N = N; prm.K = K; prm.r = r; prm.G = G;
+  const size_t smem = (size_t)kDxStages * kDxStageBytes + 1024;
+  static bool done[64] = {};
+  st = set_smem_once(gemm_w4_dx_kernel, smem, done);
+  if (st != QEFT_OK) return st;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cdiv(M, 128 * kDxTB), (unsigned)cdiv(K, kDxBF));
+  cfg.blockDim = dim3(kDxThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (flags & QEFT_F_PDL) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel, dymap, prm);
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return QEFT_OK;
+}
+
+extern "C" int qeft_dow(const void* dy, const void* x, float* dow, int M, int N, int K, int r, int dtype, int accumulate,
+                        unsigned flags, qeft_stream_t stream) {
+  if (!dy || !x || !dow) return QEFT_E_NULL;
+  if (dtype != QEFT_DT_F16) return dtype == QEFT_DT_BF16 ? QEFT_E_UNSUPPORTED : QEFT_E_DTYPE;
+  // x is the [M, K] activation (the last r columns are used) or, with K == r, the compact [M, r] copy
+  if (M <= 0 || N <= 0 || N % 128 != 0 || r <= 0 || r % 64 != 0 || r > 256 || K < r || K % 8 != 0) return QEFT_E_SHAPE;
+  if (!check_align16(dy) || !check_align16(x) || !check_align16(dow)) return QEFT_E_ALIGN;
+  CUtensorMap dymap, xomap;
+  int st = make_tmap_f16_2d(&dymap, dy, (uint64_t)M, (uint64_t)N, kDwBK);
+  if (st != QEFT_OK) return st;
+  // the outlier activations as an [M, r] matrix with row pitch K
+  st = make_tmap_f16_2d_pitched(&xomap, static_cast<const __half*>(x) + (K - r), (uint64_t)M, (uint64_t)r, (uint64_t)K, kDwBK);
+  if (st != QEFT_OK) return st;
+  DowParams prm;
+  prm.dow = dow; prm.M = M; prm.N = N; prm.r = r; prm.accumulate = accumulate;
+  const size_t smem = (size_t)kDwStages * (2 * kDwBK * 128 + (size_t)(r / 64) * kDwBK * 128) + 1024;
+  static bool done[64] = {};
+  st = set_smem_once(dow_kernel, 200 * 1024, done);
+  if (st != QEFT_OK) return st;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(N / 128));
+  cfg.blockDim = dim3(kDwThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (flags & QEFT_F_PDL) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dow_kernel, dymap, xomap, prm);
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return QEFT_OK;
+}

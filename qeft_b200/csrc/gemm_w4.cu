@@ -18,24 +18,34 @@
 //     so one activation tile feeds two MMAs (halves the L2 -> SM activation traffic).
 //   * The dense fp16 outlier columns are simply the last r/64 k-blocks: same pipeline, the dequant warps copy
 //     oweight[f, 64 b .. 64 b + 63] to TMEM unchanged; the dead int4 columns K-r..K-1 are never read.
-//   * Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane, tcgen05.commit to
-//     mbarriers), warp 2 TMEM allocator, warps 4-11 dequant (two warpgroups, one per 128-feature block) and then
-//     epilogue (tcgen05.ld, + bias, fp16, transposed through shared memory, 16-byte stores).
-#include "common.cuh"
+//   * Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane, tcgen05.commit to
+//     mbarriers), warp 2 TMEM allocator, warps 4-19 dequant (two sets of 8 warps that alternate k-blocks; in a
+//     set one warpgroup per 128-feature block) and then epilogue (tcgen05.ld, + bias, fp16, transposed through shared memory, 16-byte stores).
+#include "tc_common.cuh"
 
-#include <cuda.h>
+#include <stdlib.h>
 
 namespace qeft {
 
-constexpr int kBM = 256;          // output features per CTA (two UMMA M = 128 blocks)
-constexpr int kBN = 128;          // tokens per CTA (UMMA N)
 constexpr int kBK = 64;           // input columns per k-block (one 128-byte swizzle row of fp16)
-constexpr int kXStages = 6;       // activation ring, 16 KB each
-constexpr int kAStages = 4;       // weight ring in TMEM, 64 columns each (2 blocks x 32 columns = 64 fp16 per lane)
-constexpr int kGemmThreads = 384;
-constexpr int kXStageBytes = kBN * kBK * 2;
+constexpr int kDequantWarps = 16;
+constexpr int kGemmThreads = (4 + kDequantWarps) * 32;
 constexpr int kTmemCols = 512;
-constexpr int kTmemA0 = 256;      // first TMEM column of the weight ring (accumulators: 0..127, 128..255)
+
+// NRB: 128-feature blocks (accumulators) per CTA; BN: tokens per CTA (UMMA N)
+template <int NRB, int BN>
+struct GemmCfg {
+  static constexpr int kBM = 128 * NRB;                      // output features per CTA
+  static constexpr int kBN = BN;
+  static constexpr int kXStageBytes = BN * kBK * 2;          // one activation tile
+  static constexpr int kXStages = (160 * 1024) / kXStageBytes > 6 ? 6 : (160 * 1024) / kXStageBytes;
+  static constexpr int kTmemA0 = NRB * BN;                   // first TMEM column of the weight ring
+  static constexpr int kAStageCols = 32 * NRB;               // 64 fp16 per lane and feature block
+  static constexpr int kAStages = (kTmemCols - kTmemA0) / kAStageCols > 8 ? 8 : (kTmemCols - kTmemA0) / kAStageCols;
+  static constexpr int kSets = kDequantWarps / (4 * NRB);    // sets of dequant warps that alternate k-blocks
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static_assert(kTmemA0 + kAStages * kAStageCols <= kTmemCols, "TMEM budget");
+};
 
 struct GemmParams {
   const uint8_t* qw;       // int16 [N/4, K] as bytes
@@ -47,65 +57,9 @@ struct GemmParams {
   int M, N, K, r, G;
   int nkb_q;               // int4 k-blocks = (K - r) / 64
   int nkb;                 // + outlier k-blocks r / 64
+  int dbg;                 // QEFT_GEMM_DEBUG bits (bisecting only; results are wrong when set): 1 = no dequant
+                           // math, 2 = no activation loads
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]   (A: 128 lanes x 16 fp16 = 8 columns; B: K-major 128-byte-swizzled tile)
-__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
-        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
-        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row groups 1024
 // bytes apart.  Advancing by one UMMA_K (16 fp16 = 32 bytes) inside the swizzle row adds 2 to the address field.
@@ -119,11 +73,16 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = kBN
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
+// kind::f16 instruction descriptor (Cfg::kIdesc): D = F32, A = B = F16, both K-major, M = 128, N = BN
+// MC: clusters of two CTAs (adjacent feature blocks, same tokens) share every activation tile: each CTA loads one
+// half with a multicast TMA, both receive the whole tile -- halves the L2 -> SM activation traffic.
+template <int NRB, int BN, bool MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
+  using Cfg = GemmCfg<NRB, BN>;
+  constexpr int kBM = Cfg::kBM, kBN = Cfg::kBN, kXStages = Cfg::kXStages, kAStages = Cfg::kAStages;
+  constexpr int kXStageBytes = Cfg::kXStageBytes, kTmemA0 = Cfg::kTmemA0, kDequantSets = Cfg::kSets;
+  constexpr uint32_t kIdesc = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kXStages + 2 * kAStages + 1];
   __shared__ uint32_t s_tmem_base;
@@ -139,11 +98,11 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
 
   const int tok0 = blockIdx.x * kBN;
   const int n0 = blockIdx.y * kBM;
-  const int nrb = (p.N - n0) >= kBM ? 2 : 1;          // 128-feature blocks of this tile (N % 128 == 0)
+  const int nrb = (p.N - n0) >= kBM ? NRB : (p.N - n0) / 128;   // 128-feature blocks of this tile (N % 128 == 0)
   const int nkb = p.nkb;
 
   if (tid == 0) {
-    for (int s = 0; s < kXStages; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
+    for (int s = 0; s < kXStages; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), MC ? 2 : 1); }
     for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), 4 * nrb); mbar_init(a_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,9 +112,11 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem_base;
+  const uint32_t crank = MC ? cluster_ctarank() : 0;
   pdl_launch_dependents();
 
   if (warp == 0) {
@@ -167,8 +128,13 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         const int s = kb % kXStages, use = kb / kXStages;
         if (use > 0) mbar_wait(x_empty(s), (uint32_t)((use - 1) & 1));
         const int k0 = kb < p.nkb_q ? kb * kBK : p.K - p.r + (kb - p.nkb_q) * kBK;
+        if (p.dbg & 2) { mbar_arrive(x_full(s)); continue; }
         mbar_expect_tx(x_full(s), kXStageBytes);
-        tma_load_2d(xs0 + s * kXStageBytes, &xmap, k0, tok0, x_full(s));
+        if (MC)     // my half of the tokens, to both CTAs (the peer sends the other half)
+          tma_load_2d_mc(xs0 + s * kXStageBytes + crank * (kXStageBytes / 2), &xmap, k0, tok0 + (int)crank * (kBN / 2),
+                         x_full(s), (uint16_t)3);
+        else
+          tma_load_2d(xs0 + s * kXStageBytes, &xmap, k0, tok0, x_full(s));
       }
     }
   } else if (warp == 1) {
@@ -183,83 +149,88 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         for (int k16 = 0; k16 < kBK / 16; ++k16) {
           const uint64_t bdesc = make_b_desc(xs0 + s * kXStageBytes + k16 * 32);
           for (int rb = 0; rb < nrb; ++rb)
-            umma_ts_f16(tmem + 128 * rb, tmem + kTmemA0 + 64 * as + 32 * rb + 8 * k16, bdesc, kIdesc,
+            umma_ts_f16(tmem + kBN * rb, tmem + kTmemA0 + Cfg::kAStageCols * as + 32 * rb + 8 * k16, bdesc, kIdesc,
                         (uint32_t)((kb | k16) != 0));
         }
-        tc_commit(x_empty(s));          // both rings are free once these MMAs have read them
+        if (MC) tc_commit_mc(x_empty(s), (uint16_t)3);   // the stage is rewritten by BOTH CTAs' producers
+        else tc_commit(x_empty(s));     // both rings are free once these MMAs have read them
         tc_commit(a_empty(as));
       }
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
     // ================= dequant warps (then epilogue) =================
-    const int dw = warp - 4, rb = dw >> 2, quad = dw & 3;
+    // set ws of 8 warps handles the k-blocks kb = ws, ws + kDequantSets, ...; inside a set warp dw owns
+    // features 128 (dw / 4) + 32 (dw % 4) .. + 31 (its TMEM lane quadrant is warp % 4)
+    const int ws = (warp - 4) / (4 * NRB), dw = (warp - 4) % (4 * NRB), rb = dw >> 2, quad = dw & 3;
     if (rb < nrb) {
       const int f = n0 + 128 * rb + 32 * quad + lane;            // this lane's output feature
       const uint8_t* qrow = p.qw + (size_t)(f >> 2) * (size_t)(2 * p.K) + (size_t)((f & 3) * 32);
       const __half* owrow = p.ow ? p.ow + (size_t)f * p.r : nullptr;
       const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16);
-      // Register prefetch ring, kPF k-blocks deep (weights come from L2: ~700 cycles away, one k-block is ~500
-      // cycles of MMA), scales one group ahead, the first outlier block a few k-blocks before it is needed.
-      constexpr int kPF = 4;
-      uint4 ring[kPF][2];
-#pragma unroll
-      for (int i = 0; i < kPF; ++i) {
-        ring[i][0] = ring[i][1] = make_uint4(0, 0, 0, 0);
-        if (i < p.nkb_q) {
-          ring[i][0] = ldg_nc_v4(qrow + (size_t)i * 128);
-          ring[i][1] = ldg_nc_v4(qrow + (size_t)i * 128 + 16);
-        }
-      }
-      const int kb_per_grp = p.G / kBK;
-      auto load_scale = [&](int grp, uint32_t& s2o, uint32_t& z2o) {
-        const unsigned short sh = ldg_nc_u16(p.scales + (size_t)grp * p.N + f);
-        const unsigned short zh = ldg_nc_u16(p.szeros + (size_t)grp * p.N + f);
-        s2o = (uint32_t)sh | ((uint32_t)sh << 16);
-        z2o = (uint32_t)zh | ((uint32_t)zh << 16);
-      };
-      uint32_t s2 = 0, z2 = 0, s2n = 0, z2n = 0;
-      const int ngrp_q = (p.nkb_q + kb_per_grp - 1) / kb_per_grp;
-      if (ngrp_q > 0) load_scale(0, s2n, z2n);
-      uint32_t ob[32];                                 // one outlier k-block (64 fp16 of this lane's feature)
-      auto load_outlier = [&](int oblk) {
-        const __half* src = owrow + (size_t)oblk * kBK;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 t4 = ldg_nc_v4(src + 8 * i);
-          ob[4 * i + 0] = t4.x; ob[4 * i + 1] = t4.y; ob[4 * i + 2] = t4.z; ob[4 * i + 3] = t4.w;
-        }
-      };
-      const int ob_issue_kb = p.nkb_q > 3 ? p.nkb_q - 3 : 0;     // when the first outlier block's loads are issued
       auto publish = [&](const uint32_t (&v)[32], int kb) {
         const int as = kb % kAStages, use = kb / kAStages;
         if (use > 0) mbar_wait(a_empty(as), (uint32_t)((use - 1) & 1));
         tc_fence_after();
-        tmem_st32(lane_taddr + (uint32_t)(kTmemA0 + 64 * as + 32 * rb), v);
+        tmem_st32(lane_taddr + (uint32_t)(kTmemA0 + Cfg::kAStageCols * as + 32 * rb), v);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full(as));
       };
-      // ---- int4 k-blocks, kPF per trip so that the ring slots are compile-time registers ----
-      for (int kb0 = 0; kb0 < p.nkb_q; kb0 += kPF) {
+      // Register prefetch ring over this set's k-blocks, kPF deep (weights come from L2, ~700 cycles away; one
+      // k-block is >= 512 cycles of MMA and this set sees every kDequantSets-th), scales one group ahead.
+      constexpr int kPF = 3;
+      constexpr int kStep = kDequantSets;
+      uint4 ring[kPF][2];
+#pragma unroll
+      for (int i = 0; i < kPF; ++i) {
+        ring[i][0] = ring[i][1] = make_uint4(0, 0, 0, 0);
+        const int kb = ws + i * kStep;
+        if (kb < p.nkb_q) {
+          ring[i][0] = ldg_nc_v4(qrow + (size_t)kb * 128);
+          ring[i][1] = ldg_nc_v4(qrow + (size_t)kb * 128 + 16);
+        }
+      }
+      const int kb_per_grp = p.G / kBK;
+      uint32_t s2 = 0, z2 = 0;
+      unsigned short sn = 0, zn = 0;                   // next group's raw halves (first use a whole group later)
+      int grp = -1, grp_next = -1;
+      const __half* sp = p.scales + f;
+      const __half* zp = p.szeros + f;
+      if (ws < p.nkb_q) { grp_next = ws / kb_per_grp; sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
+      int kb_grp_end = 0;                              // first k-block of the group after `grp`
+      for (int kb0 = ws; kb0 < p.nkb_q; kb0 += kPF * kStep) {
 #pragma unroll
         for (int i = 0; i < kPF; ++i) {
-          const int kb = kb0 + i;
+          const int kb = kb0 + i * kStep;
           if (kb < p.nkb_q) {
             const uint4 c0 = ring[i][0], c1 = ring[i][1];
-            if (kb + kPF < p.nkb_q) {
-              ring[i][0] = ldg_nc_v4(qrow + (size_t)(kb + kPF) * 128);
-              ring[i][1] = ldg_nc_v4(qrow + (size_t)(kb + kPF) * 128 + 16);
+            const int kbn = kb + kPF * kStep;
+            if (kbn < p.nkb_q) {
+              ring[i][0] = ldg_nc_v4(qrow + (size_t)kbn * 128);
+              ring[i][1] = ldg_nc_v4(qrow + (size_t)kbn * 128 + 16);
             }
-            if (kb % kb_per_grp == 0) {
-              s2 = s2n; z2 = z2n;
-              const int g1 = kb / kb_per_grp + 1;
-              if (g1 < ngrp_q) load_scale(g1, s2n, z2n);
+            if (kb >= kb_grp_end) {                    // entered the prefetched group: take it, prefetch the next
+              grp = grp_next;
+              kb_grp_end = (grp + 1) * kb_per_grp;
+              s2 = (uint32_t)sn | ((uint32_t)sn << 16);
+              z2 = (uint32_t)zn | ((uint32_t)zn << 16);
+              // the next group this set will touch
+              int kbf = kb_grp_end;
+              if (kStep > 1 && ((kbf - ws) % kStep) != 0) kbf += kStep - ((kbf - ws) % kStep);
+              if (kbf < p.nkb_q) {
+                grp_next = kbf / kb_per_grp;
+                sn = ldg_nc_u16(sp + (size_t)grp_next * p.N);
+                zn = ldg_nc_u16(zp + (size_t)grp_next * p.N);
+              }
             }
-            if (p.ow && kb == ob_issue_kb) load_outlier(0);
             uint32_t v[32];
             const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            if (p.dbg & 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = w[i & 7];
+            } else
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -274,25 +245,30 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         }
       }
       // ---- outlier k-blocks: fp16 columns, copied unchanged ----
-      if (p.ow && p.nkb_q == 0) load_outlier(0);
-      for (int kb = p.nkb_q; kb < nkb; ++kb) {
+      int kbo = p.nkb_q;
+      while (((kbo - ws) % kStep) != 0) ++kbo;         // this set's first outlier k-block
+      for (int kb = kbo; kb < nkb; kb += kStep) {
         uint32_t v[32];
+        const __half* src = owrow + (size_t)(kb - p.nkb_q) * kBK;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = ob[i];
-        if (kb + 1 < nkb) load_outlier(kb + 1 - p.nkb_q);
+        for (int i = 0; i < 8; ++i) {
+          const uint4 t4 = ldg_nc_v4(src + 8 * i);
+          v[4 * i + 0] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+        }
         publish(v, kb);
       }
 
       // ---- epilogue: y^T tile (lane = feature, columns = tokens) -> + bias -> fp16 -> y[token, feature] ----
+      // the sets split the token chunks of 32
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const float bias = p.bias ? __half2float(p.bias[f]) : 0.f;
-      __half* stage = reinterpret_cast<__half*>(xs_gen + dw * 2048);         // 32 tokens x 32 features per warp
-      const int fw = n0 + 128 * rb + 32 * quad;                               // first feature of this warp
+      __half* stage = reinterpret_cast<__half*>(xs_gen + (warp - 4) * 2048);   // 32 tokens x 32 features per warp
+      const int fw = n0 + 128 * rb + 32 * quad;                                 // first feature of this warp
 #pragma unroll 1
-      for (int tc = 0; tc < kBN / 32; ++tc) {
+      for (int tc = ws; tc < kBN / 32; tc += kDequantSets) {
         uint32_t acc[32];
-        tmem_ld32(lane_taddr + (uint32_t)(128 * rb + 32 * tc), acc);
+        tmem_ld32(lane_taddr + (uint32_t)(kBN * rb + 32 * tc), acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 32; ++i) stage[i * 32 + lane] = __float2half_rn(__uint_as_float(acc[i]) + bias);
@@ -310,7 +286,9 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       tc_fence_before();
     }
   }
-  __syncthreads();
+  __syncwarp();                      // the single-lane roles rejoin their warps
+  if (MC) cluster_sync_all();        // no CTA leaves while its peer may still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
@@ -334,18 +312,67 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// 2-D map of a row-major fp16 matrix [rows, cols]: box = 64 columns (128 bytes, swizzled) x box_rows rows
-int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D map of a row-major fp16 matrix [rows, cols] with a row pitch of `pitch` elements: box = 64 columns
+// (128 bytes, swizzled) x box_rows rows
+int make_tmap_f16_2d_pitched(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return QEFT_E_UNSUPPORTED;
+  // the encoder is a driver-API call: it needs the primary context bound to THIS thread, which a thread that has
+  // only inherited torch's device bookkeeping (e.g. an autograd worker) may not have yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint64_t strides[1] = {pitch * 2};
   const cuuint32_t box[2] = {64, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? QEFT_OK : QEFT_E_UNSUPPORTED;
+}
+int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_f16_2d_pitched(map, base, rows, cols, cols, box_rows);
+}
+
+template <int NRB, int BN, bool MC>
+static int launch_gemm(const void* x, const GemmParams& prm, unsigned flags, cudaStream_t stream) {
+  using Cfg = GemmCfg<NRB, BN>;
+  CUtensorMap xmap;
+  int st = make_tmap_f16_2d(&xmap, x, (uint64_t)prm.M, (uint64_t)prm.K, MC ? BN / 2 : BN);
+  if (st != QEFT_OK) return st;
+  auto kern = gemm_w4_kernel<NRB, BN, MC>;
+  const size_t smem = (size_t)Cfg::kXStages * Cfg::kXStageBytes + 1024;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cdiv(prm.M, BN), (unsigned)cdiv(prm.N, Cfg::kBM));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (MC) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 2; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (flags & QEFT_F_PDL) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xmap, prm);
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return QEFT_OK;
 }
 
 }  // namespace qeft
@@ -362,9 +389,6 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
   if (r < 0 || r % 64 != 0 || r >= K) return QEFT_E_SHAPE;
   if (r > 0 && !oweight) return QEFT_E_NULL;
   if (!check_align16(x) || !check_align16(qweight) || !check_align16(y) || (r > 0 && !check_align16(oweight))) return QEFT_E_ALIGN;
-  CUtensorMap xmap;
-  int st = make_tmap_f16_2d(&xmap, x, (uint64_t)M, (uint64_t)K, kBN);
-  if (st != QEFT_OK) return st;
   GemmParams prm;
   prm.qw = static_cast<const uint8_t*>(qweight);
   prm.scales = static_cast<const __half*>(scales);
@@ -375,33 +399,12 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
   prm.M = M; prm.N = N; prm.K = K; prm.r = r; prm.G = G;
   prm.nkb_q = (K - r) / kBK;
   prm.nkb = prm.nkb_q + r / kBK;
-  const size_t smem = (size_t)kXStages * kXStageBytes + 1024;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_w4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cdiv(M, kBN), (unsigned)cdiv(N, kBM));
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = (flags & QEFT_F_PDL) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_w4_kernel, xmap, prm);
-  if (e != cudaSuccess) return (int)e;
-  count_launch();
-  return QEFT_OK;
+  static const int dbg_env = getenv("QEFT_GEMM_DEBUG") ? atoi(getenv("QEFT_GEMM_DEBUG")) : 0;
+  prm.dbg = dbg_env;
+  static const int cfg_env = getenv("QEFT_GEMM_CFG") ? atoi(getenv("QEFT_GEMM_CFG")) : 0;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (cfg_env == 2) return launch_gemm<2, 128, false>(x, prm, flags, cs);
+  if (cfg_env == 1 || N % 256 != 0) return launch_gemm<1, 256, false>(x, prm, flags, cs);
+  return launch_gemm<1, 256, true>(x, prm, flags, cs);   // feature blocks pair up into clusters
 }
 
-extern "C" int qeft_gemm_w4_dx(const void*, const void*, const void*, const void*, const void*, void*, int, int, int, int,
-                               int, int, unsigned, qeft_stream_t) { return QEFT_E_UNSUPPORTED; }
-extern "C" int qeft_dow(const void*, const void*, float*, int, int, int, int, int, int, unsigned, qeft_stream_t) {
-  return QEFT_E_UNSUPPORTED;
-}
