@@ -42,6 +42,28 @@ __global__ void k_hmma(int iters, float* out, long long* cycles) {
 }
 
 template <int CHAINS>
+__global__ void k_imma(int iters, float* out, long long* cycles) {
+  int acc[CHAINS][4];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+  uint32_t a0 = threadIdx.x, a1 = threadIdx.x * 3, a2 = 0x01010101, a3 = 0x02020202, b0 = 0x01020304, b1 = 0x01010101;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+      asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+r"(acc[c][0]), "+r"(acc[c][1]), "+r"(acc[c][2]), "+r"(acc[c][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  const long long t1 = clock64();
+  int s = 0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) s += acc[c][0] + acc[c][1] + acc[c][2] + acc[c][3];
+  if (s == 123456789) out[0] = (float)s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int CHAINS>
 __global__ void k_lop3(int iters, uint32_t* out, long long* cycles) {
   uint32_t v[CHAINS];
 #pragma unroll
@@ -83,6 +105,11 @@ int main() {
     run("hmma_f16acc", 1, warps, k_hmma<1, true>);
     run("hmma_f16acc", 4, warps, k_hmma<4, true>);
     run("hmma_f16acc", 8, warps, k_hmma<8, true>);
+  }
+  for (int warps : {1, 8, 16}) {
+    run("imma_u8s8_k32", 1, warps, k_imma<1>);
+    run("imma_u8s8_k32", 2, warps, k_imma<2>);
+    run("imma_u8s8_k32", 4, warps, k_imma<4>);
   }
   uint32_t* o2 = reinterpret_cast<uint32_t*>(out);
   auto run2 = [&](int chains, int warps, auto kern) {
