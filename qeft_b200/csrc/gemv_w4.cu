@@ -48,6 +48,8 @@ struct GemvPart {
   int q_begin;            // first qweight row of this part in the launch-wide numbering
 };
 
+struct GemvParams;
+typedef GemvParams GemvParamsFwd;
 struct GemvParams {
   GemvPart part[QEFT_GEMV_MAX_PARTS];
   int nparts;
@@ -63,9 +65,11 @@ struct GemvParams {
   int xstride;            // halves between batch rows of the staged x (128 nsteps + 32: rows start 16 banks apart)
   int q_lo, q_hi;         // window of launch-wide qweight rows this launch covers
   int max_tiles;          // upper bound of tiles per CTA (sizes the partial-sum slices)
+  unsigned long long* stamps;   // debug (QEFT_GEMV_STAMPS): [launch slot][8] globaltimer values of CTA 0, or null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stamp(const GemvParamsFwd& p, int i);
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -110,6 +114,14 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+__device__ __forceinline__ void stamp(const GemvParams& p, int i) {
+  if (p.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.stamps[i] = t;
+  }
+}
+
 // mma with a zero accumulator input (first k-slice of a chain)
 __device__ __forceinline__ void mma_m16n8k16_zero(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                   uint32_t b0, uint32_t b1) {
@@ -140,8 +152,9 @@ constexpr int kSlotBytes = 4 * 512 + 128;       // per warp and unit: 4 chunks o
 // rows [pa, pb)
 struct Seg { int part, t0, nt, pa, pb, cum; };
 
-// D: ring depth in units per warp.  XS: x staged in shared memory (otherwise read through L1/L2 at every use)
-template <int D, bool XS>
+// D: ring depth in units per warp.  XS: x staged in shared memory (otherwise read through L1/L2 at every use).
+// I8 (batch m <= 2, needs XS): the int4 columns run on the int8 tensor path -- see "int8 path" below.
+template <int D, bool XS, bool I8>
 __global__ void __launch_bounds__(kThreads, 2)
 gemv_w4_kernel(const GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -158,11 +171,17 @@ gemv_w4_kernel(const GemvParams p) {
 
   // ---- shared memory carve-up -----------------------------------------------------------
   uint8_t* ring = smem_raw;                                                      // [warps][D][kSlotBytes]
-  float* part = reinterpret_cast<float*>(ring + (size_t)kWarps * D * kSlotBytes);   // [max_tiles][warps][16][m]
-  float4* sums = reinterpret_cast<float4*>(part + (size_t)p.max_tiles * kWarps * 16 * m);
-                                                         // [nsteps][4]: batch columns 2t, 2t+1: {sum x, sum x, c, c}
+  // int8 path: an accumulator column is (batch row b, digit d) = 3 b + d; the outlier sums get m more columns
+  const int ncols = I8 ? 3 * m : m;
+  const int pc = I8 ? 4 * m : m;                                                 // columns of a partial-sum row
+  float* part = reinterpret_cast<float*>(ring + (size_t)kWarps * D * kSlotBytes);   // [max_tiles][warps][16][pc]
+  float4* sums = reinterpret_cast<float4*>(part + (size_t)p.max_tiles * kWarps * 16 * pc);
+                                     // [nsteps][4]: columns 2t, 2t+1: {sum x, sum x, c, c}   (I8: {coef, coef, sum x, sum x})
   __half* xs = reinterpret_cast<__half*>(sums + nsteps * 4);                     // staged x [m][xstride], dead columns zeroed
-  __half* xo = xs + (XS ? (size_t)m * p.xstride : 0);                            // staged outlier activations [m][r]
+  uint8_t* xdig = reinterpret_cast<uint8_t*>(xs);                                // I8: [nsteps][ncols][144 B] digit bytes
+  __half* xo = I8 ? reinterpret_cast<__half*>(xdig + (size_t)nsteps * ncols * 144)
+                  : xs + (XS ? (size_t)m * p.xstride : 0);                       // staged outlier activations [m][r]
+  int* xexp = reinterpret_cast<int*>(xo + (size_t)m * r);                        // I8: [nsteps][m] block exponents
   const uint32_t ring_u32 = smem_u32(ring) + (uint32_t)(warp * D * kSlotBytes);
 
   if (tid == 0) {
@@ -185,6 +204,7 @@ gemv_w4_kernel(const GemvParams p) {
     s_nseg = ns; s_ntiles = cum;
   }
   __syncthreads();
+  stamp(p, 0);
   pdl_launch_dependents();
   const int nseg = s_nseg, ntiles = s_ntiles;
   const int nunits = ntiles * upt;
@@ -260,7 +280,7 @@ gemv_w4_kernel(const GemvParams p) {
   int pu = u0;                         // next unit to prefetch
   int ptord = u0 / upt, psu = u0 - ptord * upt;
   if (u0 < u1) pf_set_tile(ptord);
-#pragma unroll
+#pragma unroll 1                       // (one copy of the issue code: the prologue runs once, instruction-cache cold)
   for (int d = 0; d < D; ++d) {
     if (pu < u1) {
       issue(ring_u32 + d * kSlotBytes, psu);
@@ -271,13 +291,151 @@ gemv_w4_kernel(const GemvParams p) {
   }
 
   // zero the partial-sum slices (a warp without a unit in a tile contributes zero)
-  for (int i = tid; i < ntiles * kWarps * 16 * m; i += kThreads) part[i] = 0.f;
+  for (int i = tid; i < ntiles * kWarps * 16 * pc; i += kThreads) part[i] = 0.f;
 
+  stamp(p, 1);
   pdl_wait();   // x (and y as a reused buffer) belong to the previous kernel until here
+  stamp(p, 2);
 
   // ---- x: staged copy and per-step sums ---------------------------------------------------------------
   const __half* xg = p.x;
-  {
+  if constexpr (I8) {
+    // ---- int8 path: x of every 128-column step as block fixed point, three signed-byte digits -------------
+    //   x_k ~= X_k 2^(e-22),  X_k = d0 + 256 d1 + 65536 d2,  d_i in [-128, 127],  2^e > max |x| of the step
+    // (exact for every element within 12 binades of the step's maximum; fp16 has 11 significant bits).  The digit
+    // bytes are stored in the byte order of the masked weight words, so that they are B fragments of
+    // mma.m16n8k32.u8.s8 as they lie: for the 32-column chunk t of a step, word c of a weight chunk masked with
+    // 0x0f0f0f0f holds k = {2c, 2c+16, 2c+1, 2c+17} and masked with 0xf0f0f0f0 holds 16 x {2c+8, 2c+24, 2c+9, 2c+25}.
+    // One pass: item = (batch row, step, chunk t, nibble position h) = 16 values (columns k0..k0+7 and k0+16..k0+23);
+    // the 8 items of a step sit in 8 adjacent lanes, which agree on the step's sum and maximum by shuffles.
+    const int live_k = nchunks * 32;
+    float4* sums4 = sums;
+    const int nitems = m * nsteps * 8;
+    // all global loads of up to kPre passes are issued before the first use (one L2 round trip, not one per pass)
+    constexpr int kPre = 4;
+    uint4 pre[kPre][2];
+    if (!p.gather) {
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        const int it = q * kThreads + tid;
+        pre[q][0] = pre[q][1] = make_uint4(0u, 0u, 0u, 0u);
+        if (it < nitems) {
+          const int sb = it >> 3, b = sb / nsteps, s = sb - b * nsteps;
+          const int k0 = s * 128 + ((it >> 1) & 3) * 32 + 8 * (it & 1);
+          if (k0 < live_k) {
+            pre[q][0] = ldg_nc_v4(xg + (size_t)b * K + k0);
+            pre[q][1] = ldg_nc_v4(xg + (size_t)b * K + k0 + 16);
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int base = 0, pass = 0; base < nitems; base += kThreads, ++pass) {   // whole warps enter together (full-mask shuffles)
+      const int it = base + tid;
+      const bool valid = it < nitems;
+      const int h = it & 1, tt = (it >> 1) & 3;
+      const int sb = valid ? (it >> 3) : 0;                        // (batch row, step) index
+      const int b = sb / nsteps, s = sb - b * nsteps;
+      const int k0 = s * 128 + tt * 32 + 8 * h;
+      const bool live = valid && k0 < live_k;                      // live_k is a multiple of 32: whole chunks
+      const __half* xrow = xg + (size_t)b * K;
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = 0u;
+      if (live) {
+        if (p.gather) {
+          __half tmp[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { tmp[j] = xrow[p.gather[k0 + j]]; tmp[8 + j] = xrow[p.gather[k0 + 16 + j]]; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = reinterpret_cast<uint32_t*>(tmp)[j];
+        } else {
+          uint4 v0, v1;
+          if (pass < kPre) {
+            // select the preloaded pair without dynamic register indexing
+            v0 = pre[0][0]; v1 = pre[0][1];
+#pragma unroll
+            for (int q = 1; q < kPre; ++q)
+              if (pass == q) { v0 = pre[q][0]; v1 = pre[q][1]; }
+          } else {
+            v0 = ldg_nc_v4(xrow + k0); v1 = ldg_nc_v4(xrow + k0 + 16);
+          }
+          w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+        }
+      }
+      float2 f[8];
+      float sum = 0.f, mx = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = half2_bits_to_float2(w[j]);
+        sum += f[j].x + f[j].y;
+        mx = fmaxf(mx, fmaxf(fabsf(f[j].x), fabsf(f[j].y)));
+      }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      // 2^e > mx: e = exponent field - 126 (fp16 inputs are normal floats or zero)
+      const int e = mx > 0.f ? (int)((__float_as_uint(mx) >> 23) & 0xff) - 126 : -100;
+      const float sc = e > -100 ? __uint_as_float((uint32_t)(127 + 22 - e) << 23) : 0.f;          // 2^(22-e)
+      if (valid) {
+        // word c of a digit row = digits of {first[2c], second[2c], first[2c+1], second[2c+1]}.
+        // X = rint(x 2^(22-e)) by the magic-number add (|X| < 2^22): bits(fma(x, sc, 1.5 2^23)) = 0x4B400000 + X.
+        // Z = X + 0x808080 has unsigned bytes b_i with X = sum (b_i - 128) 256^i, so the signed digits are the
+        // bytes of Z ^ 0x808080: three instructions per value, then byte permutes gather each digit row.
+        uint32_t dw[3][4];
+        auto digits = [&](float v) {
+          const int bits = __float_as_int(fmaf(v, sc, 12582912.f));
+          return (uint32_t)(bits + (0x00808080 - 0x4B400000)) ^ 0x00808080u;
+        };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t d0 = digits(f[c].x), d1 = digits(f[4 + c].x), d2 = digits(f[c].y), d3 = digits(f[4 + c].y);
+          dw[0][c] = prmt(prmt(d0, d1, 0x0040), prmt(d2, d3, 0x0040), 0x5410);
+          dw[1][c] = prmt(prmt(d0, d1, 0x0051), prmt(d2, d3, 0x0051), 0x5410);
+          dw[2][c] = prmt(prmt(d0, d1, 0x0062), prmt(d2, d3, 0x0062), 0x5410);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          *reinterpret_cast<uint4*>(xdig + ((size_t)s * ncols + 3 * b + d) * 144 + tt * 32 + h * 16) =
+              make_uint4(dw[d][0], dw[d][1], dw[d][2], dw[d][3]);
+        // the step's table: lane (tt, h) of the 8 writes accumulator columns ... one float4 {coef(2j), coef(2j+1), X(2j), X(2j+1)}
+        // per column pair j; columns of this batch row are 3b .. 3b+2 (digit d: coef 2^(e-22+8d)/16, X only for d = 0)
+        if ((it & 7) == 0) {
+          float* row = reinterpret_cast<float*>(sums4 + s * 4);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int col = 3 * b + d;
+            float* dst = row + (col >> 1) * 4 + (col & 1);
+            dst[0] = e > -100 ? __uint_as_float((uint32_t)(127 + e - 22 + 8 * d - 4) << 23) : 0.f;
+            dst[2] = d == 0 ? sum : 0.f;
+          }
+          if (b == m - 1)                                          // the columns no batch row owns
+            for (int col = 3 * m; col < 8; ++col) {
+              float* dst = row + (col >> 1) * 4 + (col & 1);
+              dst[0] = 0.f; dst[2] = 0.f;
+            }
+        }
+      }
+    }
+    if (r > 0) {                                                   // the outlier activations (fp16, legacy MMA)
+      for (int j = tid; j < m * (r >> 3); j += kThreads) {
+        const int b = j / (r >> 3), jj = j - b * (r >> 3);
+        const __half* xrow = xg + (size_t)b * K;
+        uint4 v;
+        if (p.gather) {
+          __half tmp[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tmp[e] = xrow[p.gather[K - r + 8 * jj + e]];
+          v = *reinterpret_cast<uint4*>(tmp);
+        } else {
+          v = ldg_nc_v4(xrow + K - r + 8 * jj);
+        }
+        *reinterpret_cast<uint4*>(xo + (size_t)b * r + 8 * jj) = v;
+      }
+    }
+  } else {
     // units of 16 halves; 8 consecutive units = one 128-column step.  Inside a unit the first 8 halves sit in
     // "low nibble" k-slots (k % 16 < 8) and the last 8 in "high nibble" slots.
     const int upr = nsteps * 8;                             // units per batch row that the int4 steps touch
@@ -349,6 +507,7 @@ gemv_w4_kernel(const GemvParams p) {
   }
   __syncthreads();
 
+  stamp(p, 3);
   // ---- the units of this warp -----------------------------------------------------------------------
   // Batch column n of the B fragment only feeds output column n, so lanes of batch rows >= m simply re-read
   // row 0 (a broadcast; their output columns are never stored): no divergence, no zero fill.
@@ -357,6 +516,9 @@ gemv_w4_kernel(const GemvParams p) {
   const uint32_t xo_lane = smem_u32(xo) + (uint32_t)((gx * r) * 2);
   const __half* xg_lane = xg + (size_t)gx * K;
   const uint32_t sums_lane = smem_u32(sums) + 16 * t;
+  // int8 path: digit column g of the B fragment (columns >= ncols re-read the last one: never stored)
+  const uint32_t xdig_lane = smem_u32(xdig) + (uint32_t)((g < ncols ? g : ncols - 1) * 144 + t * 32);
+  const uint32_t xdig_step = (uint32_t)(ncols * 144);
 
   // B fragments of step s: x[gx][128 s + 32 t .. +32], natural order
   auto load_x = [&](uint32_t (&xb)[16], int s) {
@@ -378,12 +540,18 @@ gemv_w4_kernel(const GemvParams p) {
     }
   };
 
-  float ya[4] = {0.f, 0.f, 0.f, 0.f};      // rows ra, rb x batch columns 2t, 2t+1 of the current tile
+  float ya[4] = {0.f, 0.f, 0.f, 0.f};      // rows ra, rb x accumulator columns 2t, 2t+1 of the current tile
+  float yo[4] = {0.f, 0.f, 0.f, 0.f};      // I8: the outlier units' sums (columns = batch rows 2t, 2t+1)
   auto flush = [&](int tord) {
-    float* dst = part + ((size_t)tord * kWarps + warp) * 16 * m;
-    if (2 * t < m) { dst[ra * m + 2 * t] = ya[0]; dst[rb * m + 2 * t] = ya[2]; }
-    if (2 * t + 1 < m) { dst[ra * m + 2 * t + 1] = ya[1]; dst[rb * m + 2 * t + 1] = ya[3]; }
+    float* dst = part + ((size_t)tord * kWarps + warp) * 16 * pc;
+    if (2 * t < ncols) { dst[ra * pc + 2 * t] = ya[0]; dst[rb * pc + 2 * t] = ya[2]; }
+    if (2 * t + 1 < ncols) { dst[ra * pc + 2 * t + 1] = ya[1]; dst[rb * pc + 2 * t + 1] = ya[3]; }
     ya[0] = ya[1] = ya[2] = ya[3] = 0.f;
+    if (I8) {
+      if (2 * t < m) { dst[ra * pc + ncols + 2 * t] = yo[0]; dst[rb * pc + ncols + 2 * t] = yo[2]; }
+      if (2 * t + 1 < m) { dst[ra * pc + ncols + 2 * t + 1] = yo[1]; dst[rb * pc + ncols + 2 * t + 1] = yo[3]; }
+      yo[0] = yo[1] = yo[2] = yo[3] = 0.f;
+    }
   };
 
   // one 128-column int4 step: 8 words (4 of row ra, 4 of row rb) -> 8 mma in two chains.  xc[4j + w] is the
@@ -393,6 +561,33 @@ gemv_w4_kernel(const GemvParams p) {
   // accumulate in `lo`, odd j (high nibbles, 1024+16q) in `hi`.
   // `sp`: shared address of the step's scale rows (16 scales | 16 scaled zeros) + 2 ra.
   auto int4_step = [&](const uint4& va, const uint4& vb, int s, uint32_t sp) {
+    if constexpr (I8) {
+      // int8 path: two AND masks per word (low nibbles: q, high nibbles: 16 q, both valid u8), 4 IMMA per step,
+      // exact s32 accumulation; 16 lo + hi = 16 sum(q X); y += s * coef/16 * (16 lo + hi) + sz * sum(x)
+      const uint32_t xa = xdig_lane + (uint32_t)s * xdig_step;
+      const uint4 xe = lds_v4(xa), xq = lds_v4(xa + 16);
+      float4 sm;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sm.x), "=f"(sm.y), "=f"(sm.z), "=f"(sm.w)
+                   : "r"(sums_lane + (uint32_t)(s * 64)) : "memory");
+      constexpr uint32_t kLoM = 0x0f0f0f0fu, kHiM = 0xf0f0f0f0u;
+      int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+      auto imma = [](int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      };
+      imma(lo, va.x & kLoM, vb.x & kLoM, va.y & kLoM, vb.y & kLoM, xe.x, xe.y);
+      imma(hi, va.x & kHiM, vb.x & kHiM, va.y & kHiM, vb.y & kHiM, xq.x, xq.y);
+      imma(lo, va.z & kLoM, vb.z & kLoM, va.w & kLoM, vb.w & kLoM, xe.z, xe.w);
+      imma(hi, va.z & kHiM, vb.z & kHiM, va.w & kHiM, vb.w & kHiM, xq.z, xq.w);
+      const float sa = lds_h(sp), sbv = lds_h(sp + 8), za = lds_h(sp + 32), zb = lds_h(sp + 40);
+      const float f0 = (float)(lo[0] * 16 + hi[0]), f1 = (float)(lo[1] * 16 + hi[1]);
+      const float f2 = (float)(lo[2] * 16 + hi[2]), f3 = (float)(lo[3] * 16 + hi[3]);
+      ya[0] = fmaf(sa * sm.x, f0, fmaf(za, sm.z, ya[0]));
+      ya[1] = fmaf(sa * sm.y, f1, fmaf(za, sm.w, ya[1]));
+      ya[2] = fmaf(sbv * sm.x, f2, fmaf(zb, sm.z, ya[2]));
+      ya[3] = fmaf(sbv * sm.y, f3, fmaf(zb, sm.w, ya[3]));
+      return;
+    }
     uint32_t xc[16];
     load_x(xc, s);
     float4 sm;
@@ -470,7 +665,7 @@ gemv_w4_kernel(const GemvParams p) {
             uint2 xv;
             if (XS) xv = lds_v2(xo_lane + (uint32_t)((c0 + 16 * j + 4 * t) * 2));
             else xv = ldg_nc_v2(xg_lane + K - r + c0 + 16 * j + 4 * t);
-            mma_m16n8k16_f16f32(ya, prmt(u4.x, u4.y, 0x5410), prmt(u4.x, u4.y, 0x7632), prmt(u4.z, u4.w, 0x5410),
+            mma_m16n8k16_f16f32(I8 ? yo : ya, prmt(u4.x, u4.y, 0x5410), prmt(u4.x, u4.y, 0x7632), prmt(u4.z, u4.w, 0x5410),
                                 prmt(u4.z, u4.w, 0x7632), xv.x, xv.y);
           }
         }
@@ -482,8 +677,8 @@ gemv_w4_kernel(const GemvParams p) {
             uint4 xv;
             if (XS) xv = lds_v4(xo_lane + (uint32_t)((c0 + 32 * si + 8 * t) * 2));
             else xv = ldg_nc_v4(xg_lane + K - r + c0 + 32 * si + 8 * t);
-            mma_m16n8k16_f16f32(ya, ua.x, ub.x, ua.y, ub.y, xv.x, xv.y);
-            mma_m16n8k16_f16f32(ya, ua.z, ub.z, ua.w, ub.w, xv.z, xv.w);
+            mma_m16n8k16_f16f32(I8 ? yo : ya, ua.x, ub.x, ua.y, ub.y, xv.x, xv.y);
+            mma_m16n8k16_f16f32(I8 ? yo : ya, ua.z, ub.z, ua.w, ub.w, xv.z, xv.w);
           }
         }
       }
@@ -495,6 +690,7 @@ gemv_w4_kernel(const GemvParams p) {
   }
   if (csu != 0) flush(ctord);
   cp_async_wait<0>();
+  stamp(p, 4);
 
   // ---- add the warps' slices in a fixed order, round, store the rows this CTA owns -------------------------
   __syncthreads();
@@ -509,14 +705,19 @@ gemv_w4_kernel(const GemvParams p) {
     const int q = row >> 2;
     if (q >= S.pa && q < S.pb) {
       const GemvPart& P = p.part[S.part];
-      const float* src = part + (size_t)tord * kWarps * 16 * m + rr * m + b;
+      const float* src = part + (size_t)tord * kWarps * 16 * pc + rr * pc;
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) acc += src[w * 16 * m];
+      for (int w = 0; w < kWarps; ++w) {
+        const float* sw = src + w * 16 * pc;
+        if (I8) acc += ((sw[3 * b] + sw[3 * b + 1]) + sw[3 * b + 2]) + sw[ncols + b];
+        else acc += sw[b];
+      }
       if (P.bias) acc += __half2float(P.bias[row]);
       P.y[(size_t)b * P.N + row] = __float2half_rn(acc);
     }
   }
+  stamp(p, 5);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -540,9 +741,9 @@ static int num_sms() {
   return n;
 }
 
-template <int D, bool XS>
+template <int D, bool XS, bool I8>
 static int launch_one(const GemvParams& prm, int grid, size_t smem, unsigned flags, cudaStream_t stream) {
-  auto kern = gemv_w4_kernel<D, XS>;
+  auto kern = gemv_w4_kernel<D, XS, I8>;
   static bool attr_set[64] = {};    // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -567,12 +768,23 @@ static int launch_one(const GemvParams& prm, int grid, size_t smem, unsigned fla
   return QEFT_OK;
 }
 
-template <bool XS>
+// debug timeline: QEFT_GEMV_STAMPS=1 allocates [4096][8] u64; launch i writes slot i % 4096 (read with qeft_gemv_debug_stamps)
+static unsigned long long* g_stamps = nullptr;
+static unsigned long long g_stamp_launch = 0;
+
+template <bool XS, bool I8>
 static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_t stream) {
+  static const int stamps_env = env_int("QEFT_GEMV_STAMPS", 0);
+  if (stamps_env && !g_stamps) {
+    if (cudaMalloc(&g_stamps, 4096 * 8 * sizeof(unsigned long long)) != cudaSuccess) g_stamps = nullptr;
+    else cudaMemset(g_stamps, 0, 4096 * 8 * sizeof(unsigned long long));
+  }
+  prm.stamps = g_stamps ? g_stamps + (g_stamp_launch++ % 4096) * 8 : nullptr;
   static const int depth_env = env_int("QEFT_GEMV_DEPTH", 0);
   static const int cps_env = env_int("QEFT_GEMV_CTAS_PER_SM", 0);
   const int m = prm.m;
-  const size_t xbytes = XS ? sizeof(__half) * (size_t)m * (size_t)(prm.xstride + prm.r) : 0;
+  const size_t xbytes = I8 ? (size_t)prm.nsteps * 3 * m * 144 + sizeof(__half) * (size_t)m * prm.r + sizeof(int) * (size_t)prm.nsteps * m + 16
+                           : (XS ? sizeof(__half) * (size_t)m * (size_t)(prm.xstride + prm.r) : 0);
   const size_t sums = sizeof(float) * 16 * (size_t)prm.nsteps;
   // the kernel is bound by instruction issue, not by bytes in flight: wide launches run two CTAs per SM (16 warps)
   // once every CTA still gets at least 8 qweight rows; narrow ones keep one CTA per SM so that the next launch's
@@ -580,7 +792,7 @@ static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_
   const int cps = cps_env > 0 ? cps_env : (total_q >= 2 * 8 * num_sms() ? 2 : 1);
   const int sms = num_sms() * cps;
   // rows per launch: the partial-sum slices of a CTA must fit kPartMaxBytes
-  const size_t tile_part = sizeof(float) * kWarps * 16 * (size_t)m;
+  const size_t tile_part = sizeof(float) * kWarps * 16 * (size_t)(I8 ? 4 * m : m);
   int tiles_fit = (int)(kPartMaxBytes / tile_part);
   if (tiles_fit < 3) tiles_fit = 3;
   const int q_per_cta_max = 4 * (tiles_fit - 2 * prm.nparts > 1 ? tiles_fit - 2 * prm.nparts : 1);
@@ -601,7 +813,7 @@ static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_
     int depth = (int)((budget - fixed) / ((size_t)kWarps * kSlotBytes));
     if (depth_env > 0 && depth > depth_env) depth = depth_env;
     int st;
-#define QEFT_GEMV_LAUNCH(DD) st = launch_one<DD, XS>(prm, grid, fixed + (size_t)kWarps * DD * kSlotBytes, flags, stream)
+#define QEFT_GEMV_LAUNCH(DD) st = launch_one<DD, XS, I8>(prm, grid, fixed + (size_t)kWarps * DD * kSlotBytes, flags, stream)
     if (depth >= 10) QEFT_GEMV_LAUNCH(10);
     else if (depth >= 8) QEFT_GEMV_LAUNCH(8);
     else if (depth >= 6) QEFT_GEMV_LAUNCH(6);
@@ -666,7 +878,17 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
   prm.xstride = 128 * prm.nsteps + 32;   // the int4 steps' columns (dead columns of the last step staged as zeros)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool stage = x_gather != nullptr || (size_t)m * (size_t)(K + 136) * 2 <= kStageXMaxBytes;
-  return stage ? launch_gemv<true>(prm, total_q, flags, st) : launch_gemv<false>(prm, total_q, flags, st);
+  // batch 1-2 with staged x: the int8 tensor path (half the MMAs, 16 instead of 40 unpack instructions per step)
+  static const int i8_env = env_int("QEFT_GEMV_I8", 1);
+  const size_t i8_bytes = (size_t)prm.nsteps * 3 * m * 144 + (size_t)m * r * 2;
+  if (stage && m <= 2 && i8_env != 0 && i8_bytes <= kStageXMaxBytes) return launch_gemv<true, true>(prm, total_q, flags, st);
+  return stage ? launch_gemv<true, false>(prm, total_q, flags, st) : launch_gemv<false, false>(prm, total_q, flags, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int qeft_gemv_debug_stamps(unsigned long long* host_out, int nslots) {
+  if (!g_stamps || !host_out || nslots <= 0 || nslots > 4096) return QEFT_E_NULL;
+  cudaError_t e = cudaMemcpy(host_out, g_stamps, (size_t)nslots * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? QEFT_OK : (int)e;
 }
 
 extern "C" int qeft_gemv_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
