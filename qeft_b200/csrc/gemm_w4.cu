@@ -28,7 +28,7 @@
 namespace qeft {
 
 constexpr int kBK = 64;           // input columns per k-block (one 128-byte swizzle row of fp16)
-constexpr int kDequantWarps = 16;
+constexpr int kDequantWarps = 12;
 constexpr int kGemmThreads = (4 + kDequantWarps) * 32;
 constexpr int kTmemCols = 512;
 
@@ -37,14 +37,22 @@ template <int NRB, int BN>
 struct GemmCfg {
   static constexpr int kBM = 128 * NRB;                      // output features per CTA
   static constexpr int kBN = BN;
-  static constexpr int kXStageBytes = BN * kBK * 2;          // one activation tile
-  static constexpr int kXStages = (160 * 1024) / kXStageBytes > 6 ? 6 : (160 * 1024) / kXStageBytes;
+  static constexpr int kKPS = 2;                             // 64-column k-blocks per ring stage (8 UMMAs per barrier round)
+  static constexpr int kXTileBytes = BN * kBK * 2;           // one activation tile (one k-block)
+  static constexpr int kXStageBytes = kKPS * kXTileBytes;
+  static constexpr int kXStagesMax = (192 * 1024) / kXStageBytes > 8 ? 8 : (192 * 1024) / kXStageBytes;
   static constexpr int kTmemA0 = NRB * BN;                   // first TMEM column of the weight ring
-  static constexpr int kAStageCols = 32 * NRB;               // 64 fp16 per lane and feature block
-  static constexpr int kAStages = (kTmemCols - kTmemA0) / kAStageCols > 8 ? 8 : (kTmemCols - kTmemA0) / kAStageCols;
-  static constexpr int kSets = kDequantWarps / (4 * NRB);    // sets of dequant warps that alternate k-blocks
+  static constexpr int kABlockCols = 32 * NRB;               // one k-block: 64 fp16 per lane and feature block
+  static constexpr int kAStageCols = kKPS * kABlockCols;
+  static constexpr int kAStagesMax = (kTmemCols - kTmemA0) / kAStageCols > 8 ? 8 : (kTmemCols - kTmemA0) / kAStageCols;
+  // ONE ring: stage s = activation tile s in shared memory + weight block s in tensor memory, one full / one empty
+  // barrier per stage (the MMA issuer waits once and commits once per k-block)
+  static constexpr int kStages = kXStagesMax < kAStagesMax ? kXStagesMax : kAStagesMax;
+  static constexpr int kXStages = kStages, kAStages = kStages;
+  static constexpr int kSets = kDequantWarps / (4 * NRB);    // sets of dequant warps that alternate ring stages
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static_assert(kTmemA0 + kAStages * kAStageCols <= kTmemCols, "TMEM budget");
+  static_assert(kSets >= 1 && kSets * 4 * NRB == kDequantWarps, "every dequant warp belongs to exactly one set");
 };
 
 struct GemmParams {
@@ -82,28 +90,29 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   using Cfg = GemmCfg<NRB, BN>;
   constexpr int kBM = Cfg::kBM, kBN = Cfg::kBN, kXStages = Cfg::kXStages, kAStages = Cfg::kAStages;
   constexpr int kXStageBytes = Cfg::kXStageBytes, kTmemA0 = Cfg::kTmemA0, kDequantSets = Cfg::kSets;
+  constexpr int kKPS = Cfg::kKPS, kXTileBytes = Cfg::kXTileBytes;
   constexpr uint32_t kIdesc = Cfg::kIdesc;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kXStages + 2 * kAStages + 1];
+  __shared__ __align__(8) uint64_t bars[2 * kXStages + 1];
   __shared__ uint32_t s_tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t xs0 = (smem_addr(smem_raw) + 1023u) & ~1023u;          // 1024-byte aligned stage ring
   uint8_t* xs_gen = smem_raw + (xs0 - smem_addr(smem_raw));
   const uint32_t bar0 = smem_addr(bars);
-  auto x_full = [&](int s) { return bar0 + 8 * s; };
-  auto x_empty = [&](int s) { return bar0 + 8 * (kXStages + s); };
-  auto a_full = [&](int s) { return bar0 + 8 * (2 * kXStages + s); };
-  auto a_empty = [&](int s) { return bar0 + 8 * (2 * kXStages + kAStages + s); };
-  const uint32_t acc_full = bar0 + 8 * (2 * kXStages + 2 * kAStages);
+  auto x_full = [&](int s) { return bar0 + 8 * s; };               // TMA bytes + the dequant warps' arrivals
+  auto x_empty = [&](int s) { return bar0 + 8 * (kXStages + s); };  // tcgen05.commit of the k-block's MMAs
+  auto a_full = x_full;
+  auto a_empty = x_empty;
+  const uint32_t acc_full = bar0 + 8 * (2 * kXStages);
 
   const int tok0 = blockIdx.x * kBN;
   const int n0 = blockIdx.y * kBM;
   const int nrb = (p.N - n0) >= kBM ? NRB : (p.N - n0) / 128;   // 128-feature blocks of this tile (N % 128 == 0)
   const int nkb = p.nkb;
+  const int nst = (nkb + Cfg::kKPS - 1) / Cfg::kKPS;     // ring stages
 
   if (tid == 0) {
-    for (int s = 0; s < kXStages; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), MC ? 2 : 1); }
-    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), 4 * nrb); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kXStages; ++s) { mbar_init(x_full(s), 1 + 4 * nrb); mbar_init(x_empty(s), MC ? 2 : 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -124,43 +133,48 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
       pdl_wait();                                   // x is the previous kernel's output
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kXStages, use = kb / kXStages;
+      for (int st = 0; st < nst; ++st) {
+        const int s = st % kXStages, use = st / kXStages;
         if (use > 0) mbar_wait(x_empty(s), (uint32_t)((use - 1) & 1));
-        const int k0 = kb < p.nkb_q ? kb * kBK : p.K - p.r + (kb - p.nkb_q) * kBK;
+        const int nblk = min(kKPS, nkb - st * kKPS);
         if (p.dbg & 2) { mbar_arrive(x_full(s)); continue; }
-        mbar_expect_tx(x_full(s), kXStageBytes);
-        if (MC)     // my half of the tokens, to both CTAs (the peer sends the other half)
-          tma_load_2d_mc(xs0 + s * kXStageBytes + crank * (kXStageBytes / 2), &xmap, k0, tok0 + (int)crank * (kBN / 2),
-                         x_full(s), (uint16_t)3);
-        else
-          tma_load_2d(xs0 + s * kXStageBytes, &xmap, k0, tok0, x_full(s));
+        mbar_expect_tx(x_full(s), (uint32_t)(nblk * kXTileBytes));
+        for (int j = 0; j < nblk; ++j) {
+          const int kb = st * kKPS + j;
+          const int k0 = kb < p.nkb_q ? kb * kBK : p.K - p.r + (kb - p.nkb_q) * kBK;
+          const uint32_t dst = xs0 + s * kXStageBytes + j * kXTileBytes;
+          if (MC)     // my half of the tokens, to both CTAs (the peer sends the other half)
+            tma_load_2d_mc(dst + crank * (kXTileBytes / 2), &xmap, k0, tok0 + (int)crank * (kBN / 2), x_full(s), (uint16_t)3);
+          else
+            tma_load_2d(dst, &xmap, k0, tok0, x_full(s));
+        }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kXStages, as = kb % kAStages;
-        mbar_wait(x_full(s), (uint32_t)((kb / kXStages) & 1));
-        mbar_wait(a_full(as), (uint32_t)((kb / kAStages) & 1));
+      for (int st = 0; st < nst; ++st) {
+        const int s = st % kXStages;
+        mbar_wait(x_full(s), (uint32_t)((st / kXStages) & 1));
         tc_fence_after();
+        const int nblk = min(kKPS, nkb - st * kKPS);
+        for (int j = 0; j < nblk; ++j) {
 #pragma unroll
-        for (int k16 = 0; k16 < kBK / 16; ++k16) {
-          const uint64_t bdesc = make_b_desc(xs0 + s * kXStageBytes + k16 * 32);
-          for (int rb = 0; rb < nrb; ++rb)
-            umma_ts_f16(tmem + kBN * rb, tmem + kTmemA0 + Cfg::kAStageCols * as + 32 * rb + 8 * k16, bdesc, kIdesc,
-                        (uint32_t)((kb | k16) != 0));
+          for (int k16 = 0; k16 < kBK / 16; ++k16) {
+            const uint64_t bdesc = make_b_desc(xs0 + s * kXStageBytes + j * kXTileBytes + k16 * 32);
+            for (int rb = 0; rb < nrb; ++rb)
+              umma_ts_f16(tmem + kBN * rb, tmem + kTmemA0 + Cfg::kAStageCols * s + Cfg::kABlockCols * j + 32 * rb + 8 * k16,
+                          bdesc, kIdesc, (uint32_t)((st | j | k16) != 0));
+          }
         }
         if (MC) tc_commit_mc(x_empty(s), (uint16_t)3);   // the stage is rewritten by BOTH CTAs' producers
-        else tc_commit(x_empty(s));     // both rings are free once these MMAs have read them
-        tc_commit(a_empty(as));
+        else tc_commit(x_empty(s));     // the stage (smem tiles + TMEM blocks) is free once these MMAs have read it
       }
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
     // ================= dequant warps (then epilogue) =================
-    // set ws of 8 warps handles the k-blocks kb = ws, ws + kDequantSets, ...; inside a set warp dw owns
+    // set ws handles the ring stages ws, ws + kDequantSets, ... (all k-blocks of a stage); inside a set warp dw owns
     // features 128 (dw / 4) + 32 (dw % 4) .. + 31 (its TMEM lane quadrant is warp % 4)
     const int ws = (warp - 4) / (4 * NRB), dw = (warp - 4) % (4 * NRB), rb = dw >> 2, quad = dw & 3;
     if (rb < nrb) {
@@ -168,25 +182,32 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       const uint8_t* qrow = p.qw + (size_t)(f >> 2) * (size_t)(2 * p.K) + (size_t)((f & 3) * 32);
       const __half* owrow = p.ow ? p.ow + (size_t)f * p.r : nullptr;
       const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16);
+      // write one k-block (64 fp16 of this lane's feature) into its stage; the first block of a stage waits for
+      // the stage to be free, the last one publishes the stage
       auto publish = [&](const uint32_t (&v)[32], int kb) {
-        const int as = kb % kAStages, use = kb / kAStages;
-        if (use > 0) mbar_wait(a_empty(as), (uint32_t)((use - 1) & 1));
+        const int st = kb / kKPS, j = kb - st * kKPS;
+        const int as = st % kAStages, use = st / kAStages;
+        if (j == 0 && use > 0) mbar_wait(a_empty(as), (uint32_t)((use - 1) & 1));
         tc_fence_after();
-        tmem_st32(lane_taddr + (uint32_t)(kTmemA0 + Cfg::kAStageCols * as + 32 * rb), v);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(as));
+        tmem_st32(lane_taddr + (uint32_t)(kTmemA0 + Cfg::kAStageCols * as + Cfg::kABlockCols * j + 32 * rb), v);
+        if (j == kKPS - 1 || kb == nkb - 1) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(as));
+        }
       };
-      // Register prefetch ring over this set's k-blocks, kPF deep (weights come from L2, ~700 cycles away; one
-      // k-block is >= 512 cycles of MMA and this set sees every kDequantSets-th), scales one group ahead.
-      constexpr int kPF = 3;
-      constexpr int kStep = kDequantSets;
+      // this set's k-blocks: i-th = block (i % KPS) of stage ws + (i / KPS) * sets
+      auto kb_of = [&](int i) { return (ws + (i / kKPS) * kDequantSets) * kKPS + (i % kKPS); };
+      // Register prefetch ring over this set's k-blocks, kPF deep (weights come from L2, ~700 cycles away), scales
+      // one group ahead.
+      constexpr int kPF = 4;
+      static_assert(kPF % kKPS == 0, "ring slots must be compile-time registers");
       uint4 ring[kPF][2];
 #pragma unroll
       for (int i = 0; i < kPF; ++i) {
         ring[i][0] = ring[i][1] = make_uint4(0, 0, 0, 0);
-        const int kb = ws + i * kStep;
+        const int kb = kb_of(i);
         if (kb < p.nkb_q) {
           ring[i][0] = ldg_nc_v4(qrow + (size_t)kb * 128);
           ring[i][1] = ldg_nc_v4(qrow + (size_t)kb * 128 + 16);
@@ -198,38 +219,49 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       int grp = -1, grp_next = -1;
       const __half* sp = p.scales + f;
       const __half* zp = p.szeros + f;
-      if (ws < p.nkb_q) { grp_next = ws / kb_per_grp; sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
-      int kb_grp_end = 0;                              // first k-block of the group after `grp`
-      for (int kb0 = ws; kb0 < p.nkb_q; kb0 += kPF * kStep) {
+      {
+        const int kb = kb_of(0);
+        if (kb < p.nkb_q) { grp_next = kb / kb_per_grp; sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
+      }
+      bool done = false;
+      for (int i0 = 0; !done; i0 += kPF) {
 #pragma unroll
-        for (int i = 0; i < kPF; ++i) {
-          const int kb = kb0 + i * kStep;
+        for (int u = 0; u < kPF; ++u) {
+          const int i = i0 + u;
+          const int kb = kb_of(i);
+          if (kb >= nkb) { done = true; break; }
+          uint32_t v[32];
           if (kb < p.nkb_q) {
-            const uint4 c0 = ring[i][0], c1 = ring[i][1];
-            const int kbn = kb + kPF * kStep;
+            const uint4 c0 = ring[u][0], c1 = ring[u][1];
+            const int kbn = kb_of(i + kPF);
             if (kbn < p.nkb_q) {
-              ring[i][0] = ldg_nc_v4(qrow + (size_t)kbn * 128);
-              ring[i][1] = ldg_nc_v4(qrow + (size_t)kbn * 128 + 16);
+              ring[u][0] = ldg_nc_v4(qrow + (size_t)kbn * 128);
+              ring[u][1] = ldg_nc_v4(qrow + (size_t)kbn * 128 + 16);
             }
-            if (kb >= kb_grp_end) {                    // entered the prefetched group: take it, prefetch the next
-              grp = grp_next;
-              kb_grp_end = (grp + 1) * kb_per_grp;
-              s2 = (uint32_t)sn | ((uint32_t)sn << 16);
-              z2 = (uint32_t)zn | ((uint32_t)zn << 16);
-              // the next group this set will touch
-              int kbf = kb_grp_end;
-              if (kStep > 1 && ((kbf - ws) % kStep) != 0) kbf += kStep - ((kbf - ws) % kStep);
-              if (kbf < p.nkb_q) {
-                grp_next = kbf / kb_per_grp;
-                sn = ldg_nc_u16(sp + (size_t)grp_next * p.N);
-                zn = ldg_nc_u16(zp + (size_t)grp_next * p.N);
+            const int g_now = kb / kb_per_grp;
+            if (g_now != grp) {                        // entered a new group: take the prefetched pair (or load it)
+              if (g_now == grp_next) {
+                s2 = (uint32_t)sn | ((uint32_t)sn << 16);
+                z2 = (uint32_t)zn | ((uint32_t)zn << 16);
+              } else {
+                const unsigned short a = ldg_nc_u16(sp + (size_t)g_now * p.N), bq = ldg_nc_u16(zp + (size_t)g_now * p.N);
+                s2 = (uint32_t)a | ((uint32_t)a << 16);
+                z2 = (uint32_t)bq | ((uint32_t)bq << 16);
               }
+              grp = g_now;
+              // the next group this set will touch: look ahead over its coming k-blocks
+              grp_next = -1;
+#pragma unroll
+              for (int a = 1; a <= 2 * kKPS; ++a) {
+                const int kba = kb_of(i + a);
+                if (grp_next < 0 && kba < p.nkb_q && kba / kb_per_grp != g_now) grp_next = kba / kb_per_grp;
+              }
+              if (grp_next >= 0) { sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
             }
-            uint32_t v[32];
             const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
             if (p.dbg & 1) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = w[i & 7];
+              for (int q = 0; q < 32; ++q) v[q] = w[q & 7];
             } else
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -240,22 +272,17 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[16 * h + c + 4 * j] = hfma2_u32(hq[j], s2, z2);   // w = fma(q, s, sz)
               }
-            publish(v, kb);
-          }
-        }
-      }
-      // ---- outlier k-blocks: fp16 columns, copied unchanged ----
-      int kbo = p.nkb_q;
-      while (((kbo - ws) % kStep) != 0) ++kbo;         // this set's first outlier k-block
-      for (int kb = kbo; kb < nkb; kb += kStep) {
-        uint32_t v[32];
-        const __half* src = owrow + (size_t)(kb - p.nkb_q) * kBK;
+          } else {
+            // outlier k-block: fp16 columns, copied unchanged
+            const __half* src = owrow + (size_t)(kb - p.nkb_q) * kBK;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 t4 = ldg_nc_v4(src + 8 * i);
-          v[4 * i + 0] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+            for (int q = 0; q < 8; ++q) {
+              const uint4 t4 = ldg_nc_v4(src + 8 * q);
+              v[4 * q + 0] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+            }
+          }
+          publish(v, kb);
         }
-        publish(v, kb);
       }
 
       // ---- epilogue: y^T tile (lane = feature, columns = tokens) -> + bias -> fp16 -> y[token, feature] ----
@@ -403,8 +430,9 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
   prm.dbg = dbg_env;
   static const int cfg_env = getenv("QEFT_GEMM_CFG") ? atoi(getenv("QEFT_GEMM_CFG")) : 0;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  if (cfg_env == 2) return launch_gemm<2, 128, false>(x, prm, flags, cs);
-  if (cfg_env == 1 || N % 256 != 0) return launch_gemm<1, 256, false>(x, prm, flags, cs);
-  return launch_gemm<1, 256, true>(x, prm, flags, cs);   // feature blocks pair up into clusters
+  // QEFT_GEMM_CFG=3: 2-CTA clusters multicast every activation tile (halves the L2 reads; measured 2-5 % slower than
+  // the plain launch on B200 because L2 bandwidth is not the limiter at these sizes, so it is not the default)
+  if (cfg_env == 3 && N % 256 == 0) return launch_gemm<1, 256, true>(x, prm, flags, cs);
+  return launch_gemm<1, 256, false>(x, prm, flags, cs);
 }
 
