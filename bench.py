@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gemm", action="store_true", help="also time the prefill GEMM (M=2048) and report TFLOP/s")
+    ap.add_argument("--no-gemm", action="store_true", help="skip the prefill GEMM / backward extras (M=2048 TFLOP/s)")
     return ap.parse_args()
 
 
@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "50", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -102,12 +102,17 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(avg_alg_bytes_per_launch):
+    """DRAM bytes per launch from the committed `ncu --set full` capture of the dominant kernel
+    (profiles/gemv_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum and the algorithmic bytes of the
+    profiled launch).  The bench's launches have four shapes, so the per-launch figure reported beside `achieved`
+    is the measured traffic / algorithmic ratio applied to this run's average algorithmic bytes per launch."""
     p = os.path.join(ROOT, "profiles", "gemv_traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f)
-    return None
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d["dram_bytes"] / d["algorithmic_bytes"] * avg_alg_bytes_per_launch
 
 
 # --------------------------------------------------------------------------------------------------
@@ -234,14 +239,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
     nbytes = stack.algorithmic_bytes_per_step()
+    launches_per_step = stack.launches_per_step()
+    workload_layers, workload_fused, workload_pdl, workload_graph = stack.nlayers, stack.fused, stack.pdl, stack.graph is not None
     tot = torch.tensor([nbytes], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     nbytes_all = tot.item()
 
     extra = {}
-    if args.gemm and rank == 0:
-        extra["gemm"] = bench_gemm(model)
+    if not args.no_gemm and rank == 0 and world == 1:
+        del stack
+        torch.cuda.empty_cache()
+        extra["prefill_finetune"] = bench_gemm(model)
+        stack = None
 
     if rank == 0:
         ms_step = ms / args.steps
@@ -254,12 +264,12 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {
-                "workload": (f"llama2-{model} decode b{args.batch}: {stack.nlayers} decoder blocks x 7 packed QuantLinear "
-                             f"(w4 g128 r128) = {stack.launches_per_step()} GEMV launches/token"
+                "workload": (f"llama2-{model} decode b{args.batch}: {workload_layers} decoder blocks x 7 packed QuantLinear "
+                             f"(w4 g128 r128) = {launches_per_step} GEMV launches/token"
                              + (f", column-sharded over {world} ranks + NCCL all-gather" if world > 1 else "")),
                 "algorithmic_bytes_per_step": int(nbytes_all), "l2_policy": "inputs larger than L2 (3.7 GB of weights streamed per step)",
-                "cuda_graph": stack.graph is not None, "fused_qkv_gateup": stack.fused, "pdl": stack.pdl,
-                "layers": stack.nlayers,
+                "cuda_graph": workload_graph, "fused_qkv_gateup": workload_fused, "pdl": workload_pdl,
+                "layers": workload_layers,
             },
             "decode_tok_s": args.batch * 1e3 / ms_step,
             "clocks": clocks,
@@ -268,7 +278,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
                          "frac_of_nominal_8TBs": per_gpu / 8000.0, "peak_source": peak_src, "kernel": "gemv_w4_kernel",
-                         "traffic": ncu_traffic()},
+                         "traffic": ncu_traffic(nbytes_all / world / launches_per_step),
+                         "traffic_unit": "bytes per launch (ncu dram read+write of the profiled launch, scaled by algorithmic bytes)",
+                         "algorithmic_bytes_per_launch": nbytes_all / world / launches_per_step},
         }
         if args.layers is not None:
             line["config"]["INVALID"] = "reduced layer count (debug run)"
@@ -278,15 +290,58 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": nb / tmed / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
                                     "sample": f"one llama2-{model} decoder block (7 dequant+matmul calls, {nb} algorithmic bytes), "
                                               f"median of {len(times)} after 1 warm-up; {tmed:.3f} s per block",
-                                    "tok_s_extrapolated": 1.0 / (tmed * stack.nlayers)}
+                                    "tok_s_extrapolated": 1.0 / (tmed * workload_layers)}
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_gemm(model):
-    return None
+def bench_gemm(model, M=2048, iters=10):
+    """Configs 3 and 4 of BASELINE.json beside the headline: per-shape prefill GEMM (fused outliers + bias path) and
+    backward (dX, dOW) TFLOP/s at M = 2048 tokens, against the measured bf16 tensor peak."""
+    import torch
+
+    from qeft_b200 import qeft_cuda
+    from qeft_b200.synth import LLAMA_SHAPES, synth_tensors
+
+    _, tpeak, src = measured_peaks()
+    h, f, _, kv = LLAMA_SHAPES[model]
+    shapes = [("qkv/o_proj", h, h), ("gate/up_proj", f, h), ("down_proj", h, f)]
+    out = {"M": M, "tensor_peak_TFLOPs": tpeak, "peak_source": src, "dtype": "f16", "shapes": []}
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / iters
+
+    for name, N, K in shapes:
+        t = synth_tensors(N, K, seed=7)
+        x = torch.randn(M, K, device="cuda").half()
+        dy = torch.randn(M, N, device="cuda").half()
+        y = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        dx = torch.empty(M, K, device="cuda", dtype=torch.float16)
+        dow = torch.empty(N, 128, device="cuda", dtype=torch.float32)
+        xo = x[:, K - 128:].contiguous()
+        flops = 2.0 * M * N * K
+        tf = timeit(lambda: qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, out=y, pdl=False))
+        tb = timeit(lambda: qeft_cuda.gemm_w4_dx(dy, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], K, out=dx, pdl=False))
+        tw = timeit(lambda: qeft_cuda.dow(dy, xo, 128, out=dow))
+        out["shapes"].append({"name": name, "N": N, "K": K,
+                              "fwd_TFLOPs": flops / tf / 1e12, "fwd_frac": flops / tf / 1e12 / tpeak,
+                              "dx_TFLOPs": flops / tb / 1e12, "dx_frac": flops / tb / 1e12 / tpeak,
+                              "dow_us": tw * 1e6,
+                              "finetune_step_TFLOPs": (2 * flops + 2.0 * M * N * 128) / (tf + tb + tw) / 1e12})
+        del t, x, dy, y, dx
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():

@@ -1,0 +1,126 @@
+"""Model-level parity: a tiny random-init Llama whose decoder linears are packed QuantLinear layers.
+
+SURVEY.md 8(c)(5): synthetic-token perplexity through our kernels (prefill = tcgen05 GEMM, decode = GEMV) against
+the same fp16 model whose linears are dense `nn.Linear` layers holding the dequantised weights ("reference dequant +
+matmul"), plus one fine-tuning step through `QuantMatMulQEFT` against autograd through the dense model.  Needs a B200.
+"""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+R, G = 64, 128
+
+
+def build_models(seed=0, layers=2, hidden=256, ffn=512, vocab=320):
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from qeft_b200 import qeft_cuda
+    from qeft_b200.qlinear import QuantLinear
+    from qeft_b200.quant import find_layers, make_quant
+    from qeft_b200.synth import synth_tensors
+
+    torch.manual_seed(seed)
+    cfg = LlamaConfig(hidden_size=hidden, intermediate_size=ffn, num_hidden_layers=layers, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=vocab, max_position_embeddings=256, tie_word_embeddings=False)
+    packed = LlamaForCausalLM(cfg).half().cuda().eval()
+    dense = LlamaForCausalLM(cfg).half().cuda().eval()
+    dense.load_state_dict(packed.state_dict())
+    names = [n for n in find_layers(packed, [torch.nn.Linear]) if "layers." in n]
+    infos = {n: Namespace(bits=4, n_out=R, group_size=G, reorder=True, sym=False) for n in names}
+    make_quant(packed, infos)
+    qlayers = find_layers(packed, [QuantLinear])
+    assert sorted(qlayers) == sorted(names)
+    dense_linears = find_layers(dense, [torch.nn.Linear])
+    for i, (name, q) in enumerate(sorted(qlayers.items())):
+        t = synth_tensors(q.outfeatures, q.infeatures, r=R, G=G, seed=100 + i, o_proj=("o_proj" in name))
+        for k, v in t.items():
+            setattr(q, k, v)
+        q.set_kernel(False)
+        # the dense twin: dequantised int4 columns, outlier columns replaced by oweight; o_proj consumes the input
+        # in model order, i.e. column reorder_ids[j] of the dense weight is column j of the packed layer
+        W = qeft_cuda.dequant_w4(q.qweight, q.scales, q.scaled_zeros, q.oweight, G)
+        if hasattr(q, "reorder_ids"):
+            Wm = torch.empty_like(W)
+            Wm[:, q.reorder_ids] = W
+            W = Wm
+        dense_linears[name].weight.data = W.contiguous()
+    return packed, dense, cfg
+
+
+def nll(model, tokens):
+    with torch.no_grad():
+        logits = model(tokens).logits.float()
+    return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), tokens[:, 1:].reshape(-1)).item()
+
+
+def test_prefill_perplexity_matches_dense_reference():
+    packed, dense, cfg = build_models()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    tokens = torch.randint(0, cfg.vocab_size, (2, 128), device="cuda", generator=g)
+    a, b = nll(packed, tokens), nll(dense, tokens)
+    ppl_a, ppl_b = float(np.exp(a)), float(np.exp(b))
+    print(f"prefill: nll packed {a:.6f} dense {b:.6f}; ppl {ppl_a:.4f} vs {ppl_b:.4f}")
+    assert abs(a - b) < 5e-4                      # log-perplexity to three decimals
+    assert abs(ppl_a - ppl_b) / ppl_b < 1e-3
+
+
+def test_decode_perplexity_matches_prefill():
+    """Token-by-token decode (seq_len < 8 -> GEMV, KV cache) scores the same tokens as one prefill pass."""
+    packed, dense, cfg = build_models(seed=1)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2)
+    tokens = torch.randint(0, cfg.vocab_size, (1, 48), device="cuda", generator=g)
+    with torch.no_grad():
+        full = packed(tokens).logits.float()
+        past, rows = None, []
+        for i in range(tokens.shape[1]):
+            out = packed(tokens[:, i:i + 1], past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            rows.append(out.logits.float())
+        step = torch.cat(rows, dim=1)
+    ce = torch.nn.functional.cross_entropy
+    a = ce(full[:, :-1].reshape(-1, full.shape[-1]), tokens[:, 1:].reshape(-1)).item()
+    b = ce(step[:, :-1].reshape(-1, step.shape[-1]), tokens[:, 1:].reshape(-1)).item()
+    print(f"decode: nll prefill {a:.6f} decode {b:.6f}")
+    assert abs(a - b) < 5e-4
+
+
+def test_finetune_step_matches_dense_autograd():
+    """One fwd+bwd step with trainable outlier columns: loss and oweight gradients against the dense twin."""
+    from qeft_b200.qlinear import QuantLinear
+    from qeft_b200.quant import find_layers
+    packed, dense, cfg = build_models(seed=2)
+    qlayers = find_layers(packed, [QuantLinear])
+    for p in packed.parameters():
+        p.requires_grad_(False)
+    for q in qlayers.values():
+        q.set_kernel(True)
+        q.set_for_wct()
+    packed.train()
+    dense.train()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    tokens = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda", generator=g)
+    out_p = packed(tokens, labels=tokens)
+    out_p.loss.backward()
+    out_d = dense(tokens, labels=tokens)
+    out_d.loss.backward()
+    assert abs(out_p.loss.item() - out_d.loss.item()) < 2e-3
+    dense_linears = find_layers(dense, [torch.nn.Linear])
+    checked = 0
+    for name, q in qlayers.items():
+        assert q.oweight.grad is not None and q.oweight.grad.dtype == torch.float32
+        gd = dense_linears[name].weight.grad.float()
+        if hasattr(q, "reorder_ids"):
+            gd = gd[:, q.reorder_ids]
+        want = gd[:, -R:]
+        got = q.oweight.grad
+        denom = want.abs().max().item() + 1e-8
+        assert (got - want).abs().max().item() / denom < 3e-2, name      # fp16 model, different accumulation orders
+        checked += 1
+    assert checked == len(qlayers)
