@@ -186,7 +186,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     model = args.model or ("7b" if world == 1 else "70b")
     stack = PackedDecoderStack(model, layers=args.layers, fused=not args.no_fused, pdl=not args.no_pdl,
-                               shard=(rank, world), batch=args.batch, device=f"cuda:{local}")
+                               shard=(rank, world), batch=args.batch, device=f"cuda:{local}", fast_synth=True)
     if world > 1:
         stack.enable_allgather(dist.group.WORLD)
     if not args.no_graph:

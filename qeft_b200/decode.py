@@ -25,7 +25,7 @@ from .synth import LLAMA_SHAPES, synth_tensors
 
 class PackedDecoderStack:
     def __init__(self, model="7b", layers=None, r=128, G=128, device="cuda", seed=0, fused=True, pdl=True,
-                 shard=(0, 1), batch=1):
+                 shard=(0, 1), batch=1, fast_synth=False):
         h, f, nl, kv = LLAMA_SHAPES[model]
         self.model, self.r, self.G, self.device = model, r, G, torch.device(device)
         self.h, self.f, self.kv = h, f, kv
@@ -46,7 +46,7 @@ class PackedDecoderStack:
                                                ("o", self.no, h), ("gate", self.nf, h), ("up", self.nf, h),
                                                ("down", self.no, f))):
                 blk[name] = synth_tensors(N, K, r, G, seed=seed * 100003 + li * 16 + pi + rank * 7919,
-                                          device=self.device, o_proj=(name == "o"))
+                                          device=self.device, o_proj=(name == "o"), fast=fast_synth)
                 blk[name]["N"] = N
             if r > 0:   # o_proj gathers its outlier channels to the back (qlinear.py:273-275): fused into the GEMV
                 blk["o"]["reorder_ids32"] = sparse_to_dense_ids(blk["o"]["outlieridx"], h).to(torch.int32)

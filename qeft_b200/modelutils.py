@@ -83,3 +83,37 @@ def replace_oweight(model, ckpt_wct):
             module.oweight.data = sd[name].data.to(device=module.oweight.device, dtype=module.oweight.dtype)
             module.refresh_oweight_interleaved()
     return model
+
+
+# --------------------------------------------------------------------------------------------------
+# column (output-feature) sharding of one packed layer -- SURVEY.md 8(e)
+# --------------------------------------------------------------------------------------------------
+def shard_rows(N, rank, world, multiple=128):
+    """Rows ``[lo, hi)`` of an N-row layer owned by ``rank``: contiguous, equal, a multiple of ``multiple`` each
+    (128 for the tensor-core tiles; the GEMV alone needs 8)."""
+    if N % (world * multiple) != 0:
+        raise ValueError(f"N={N} does not split into {world} shards of a multiple of {multiple} rows")
+    per = N // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_layer_tensors(t, rank, world, multiple=128):
+    """The rank's slice of a packed layer's tensors (dict with the checkpoint's buffer names).
+
+    No repacking: the interleave groups are 4 rows (qweight) / 8 rows (oweight_interleaved), so a row range that is
+    a multiple of 8 is a contiguous slab of every buffer.  x is replicated; rank p computes ``y[:, lo:hi]``;
+    the slices are concatenated along the feature dimension by one all-gather per launch group."""
+    N = t["qweight"].shape[0] * 4
+    lo, hi = shard_rows(N, rank, world, multiple)
+    out = {"qweight": t["qweight"][lo // 4:hi // 4].contiguous(),
+           "scales": t["scales"][:, lo:hi].contiguous(),
+           "scaled_zeros": t["scaled_zeros"][:, lo:hi].contiguous()}
+    if t.get("bias") is not None:
+        out["bias"] = t["bias"][lo:hi].contiguous()
+    if t.get("oweight") is not None:
+        out["oweight"] = t["oweight"][lo:hi].contiguous()
+    if t.get("oweight_interleaved") is not None:
+        out["oweight_interleaved"] = t["oweight_interleaved"][lo // 2:hi // 2].contiguous()
+    if t.get("outlieridx") is not None:
+        out["outlieridx"] = t["outlieridx"]
+    return out

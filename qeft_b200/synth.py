@@ -26,19 +26,28 @@ def decoder_linears(model: str):
 
 
 @torch.no_grad()
-def synth_tensors(N, K, r=128, G=128, seed=0, device="cuda", bias=False, o_proj=False):
-    """Packed tensors of one layer: q ~ U{0..15}, scale ~ U(0.002, 0.012), zero ~ U{0..15}, oweight ~ N(0, 0.02^2)."""
+def synth_tensors(N, K, r=128, G=128, seed=0, device="cuda", bias=False, o_proj=False, fast=False):
+    """Packed tensors of one layer: q ~ U{0..15}, scale ~ U(0.002, 0.012), zero ~ U{0..15}, oweight ~ N(0, 0.02^2).
+
+    ``fast``: draw the packed int16 words directly (uniform random nibbles, which is what packing uniform q gives; the
+    dead outlier columns then hold random nibbles instead of the zero point, and no kernel reads them).  Used by the
+    benchmark stacks, where generating and packing 35 GB of int32 weights would dominate the run."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     ng = K // G
-    q = torch.randint(0, 16, (N, K), dtype=torch.int32, device=device, generator=gen)
     zero = torch.randint(0, 16, (ng, N), dtype=torch.int32, device=device, generator=gen)
     scale = (torch.rand((ng, N), device=device, generator=gen) * 0.010 + 0.002).half()
-    if r > 0:
-        cols = torch.arange(K - r, K, device=device)
-        q[:, K - r:] = zero[cols // G, :].t()
+    if fast:
+        qweight = torch.randint(-32768, 32768, (N // 4, K), dtype=torch.int16, device=device, generator=gen)
+        q = None
+    else:
+        q = torch.randint(0, 16, (N, K), dtype=torch.int32, device=device, generator=gen)
+        if r > 0:
+            cols = torch.arange(K - r, K, device=device)
+            q[:, K - r:] = zero[cols // G, :].t()
+        qweight = qeft_cuda.pack_w4(q)
     out = {
-        "qweight": qeft_cuda.pack_w4(q),
+        "qweight": qweight,
         "scales": scale,
         "scaled_zeros": (-(zero.float() * scale.float())).half(),
     }
