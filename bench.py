@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["fused", "nccl"],
+                    help="N > 1: one NCCL all-gather per launch group (default; measured faster at N = 2 this round) or the "
+                         "all-gather fused into the GEMV epilogue (peer stores over NVLink + arrival counters)")
     ap.add_argument("--no-gemm", action="store_true", help="skip the prefill GEMM / backward extras (M=2048 TFLOP/s)")
     return ap.parse_args()
 
@@ -188,7 +191,10 @@ def run_ours(args):
     stack = PackedDecoderStack(model, layers=args.layers, fused=not args.no_fused, pdl=not args.no_pdl,
                                shard=(rank, world), batch=args.batch, device=f"cuda:{local}", fast_synth=True)
     if world > 1:
-        stack.enable_allgather(dist.group.WORLD)
+        if args.gather == "fused":
+            stack.enable_fused_gather(dist.group.WORLD)
+        else:
+            stack.enable_allgather(dist.group.WORLD)
     if not args.no_graph:
         stack.capture()
 
@@ -266,7 +272,9 @@ def run_ours(args):
             "config": {
                 "workload": (f"llama2-{model} decode b{args.batch}: {workload_layers} decoder blocks x 7 packed QuantLinear "
                              f"(w4 g128 r128) = {launches_per_step} GEMV launches/token"
-                             + (f", column-sharded over {world} ranks + NCCL all-gather" if world > 1 else "")),
+                             + (f", column-sharded over {world} ranks, all-gather "
+                                + ("fused into the GEMV epilogue (peer stores over NVLink)" if args.gather == "fused" else "by NCCL")
+                                if world > 1 else "")),
                 "algorithmic_bytes_per_step": int(nbytes_all), "l2_policy": "inputs larger than L2 (3.7 GB of weights streamed per step)",
                 "cuda_graph": workload_graph, "fused_qkv_gateup": workload_fused, "pdl": workload_pdl,
                 "layers": workload_layers,
@@ -294,7 +302,17 @@ def run_ours(args):
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a captured graph keeps NCCL work alive: drop it before the communicator, and never let teardown hang the box
+        import threading
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        sys.stdout.flush()
+        if stack is not None:
+            stack.graph = None
+        del stack
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def bench_gemm(model, M=2048, iters=10):

@@ -102,6 +102,31 @@ QEFT_API int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, in
                        qeft_stream_t stream);
 
 /*
+ * Column-sharded decode (no reference counterpart: the reference has no multi-GPU code): the same
+ * multi-projection GEMV, but every rank computes its slice of the output features and the kernel's epilogue stores
+ * that slice DIRECTLY into the gathered buffer of every rank (peer-mapped pointers over NVLink) -- an all-gather
+ * fused into the GEMV, no collective call.  Completion is signalled per launch: the last CTA of the launch adds 1
+ * (release, system scope) to every rank's arrival counter `done_peer[p]`; a dependent launch passes that counter
+ * as `wait_flag` and spins (acquire, system scope) until it reaches `*epoch * nranks` before it reads its input.
+ * `epoch` is a device-resident step counter the caller increments once per decode step (graph-replay friendly).
+ * `local_count` is a zero-initialised device word private to this launch (CTA arrival count).
+ */
+#define QEFT_MAX_RANKS 8
+typedef struct {
+  int nranks;
+  int y_ld;                                            /* elements between batch rows of the gathered buffers */
+  void* y_peer[QEFT_MAX_RANKS][QEFT_GEMV_MAX_PARTS];   /* rank p's buffer for part i, offset to THIS rank's columns */
+  uint32_t* done_peer[QEFT_MAX_RANKS];                 /* rank p's arrival counter of this launch */
+  uint32_t* local_count;
+  const uint32_t* wait_flag;                           /* local arrival counter of the launch depended on, or NULL */
+  const uint32_t* epoch;
+} qeft_gather_t;
+
+QEFT_API int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,
+                              const int32_t* x_gather, int m, int K, int r, int G, unsigned flags,
+                              const qeft_gather_t* gather, qeft_stream_t stream);
+
+/*
  * Prefill / fine-tune GEMM:  y[M, N] = x[M, K] . Wdense^T (+ bias)  on tcgen05 tensor cores.
  * Replaces  gemm_4bit (qeft/kernel/quantization_new/gemm/gemm_cuda.cu:929-1033)  PLUS the separate
  * `y += F.linear(x[..., -r:], oweight)` and `y + bias` of qeft/qlinear.py:264-268 in one kernel.

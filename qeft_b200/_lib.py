@@ -21,6 +21,16 @@ class GemvPart(C.Structure):
                 ("oweight", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p), ("N", C.c_int)]
 
 
+MAX_RANKS = 8
+
+
+class Gather(C.Structure):
+    _fields_ = [("nranks", C.c_int), ("y_ld", C.c_int),
+                ("y_peer", (C.c_void_p * GEMV_MAX_PARTS) * MAX_RANKS),
+                ("done_peer", C.c_void_p * MAX_RANKS),
+                ("local_count", C.c_void_p), ("wait_flag", C.c_void_p), ("epoch", C.c_void_p)]
+
+
 _vp, _i, _u = C.c_void_p, C.c_int, C.c_uint
 # name -> (restype, argtypes): every symbol include/qeft_b200.h declares
 SIGNATURES = {
@@ -30,6 +40,7 @@ SIGNATURES = {
     "qeft_status_string": (C.c_char_p, [_i]),
     "qeft_gemv_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemv_w4_multi": (_i, [_vp, C.POINTER(GemvPart), _i, _i, _vp, _i, _i, _i, _i, _u, _vp]),
+    "qeft_gemv_w4_multi_gather": (_i, [_vp, C.POINTER(GemvPart), _i, _i, _vp, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),
     "qeft_gemm_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemm_w4_dx": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_dow": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),

@@ -66,6 +66,14 @@ struct GemvParams {
   int q_lo, q_hi;         // window of launch-wide qweight rows this launch covers
   int max_tiles;          // upper bound of tiles per CTA (sizes the partial-sum slices)
   unsigned long long* stamps;   // debug (QEFT_GEMV_STAMPS): [launch slot][8] globaltimer values of CTA 0, or null
+  // fused all-gather (column-sharded decode): results go to every rank's gathered buffer
+  int nranks;                   // 0: plain launch (part.y)
+  int y_ld;
+  __half* y_peer[QEFT_MAX_RANKS][QEFT_GEMV_MAX_PARTS];
+  uint32_t* done_peer[QEFT_MAX_RANKS];
+  uint32_t* local_count;
+  const uint32_t* wait_flag;
+  const uint32_t* epoch;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -295,6 +303,18 @@ gemv_w4_kernel(const GemvParams p) {
 
   stamp(p, 1);
   pdl_wait();   // x (and y as a reused buffer) belong to the previous kernel until here
+  if (p.wait_flag) {
+    // column-sharded chain: the launch this one depends on has finished on THIS rank (stream order); wait until every
+    // rank's slice of its output has landed here: its arrival counter reaches epoch x ranks
+    if (tid == 0) {
+      const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.epoch) * (uint32_t)p.nranks;
+      uint32_t got;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.wait_flag) : "memory");
+      } while ((int)(got - want) < 0);
+    }
+    __syncthreads();
+  }
   stamp(p, 2);
 
   // ---- x: staged copy and per-step sums ---------------------------------------------------------------
@@ -714,7 +734,26 @@ gemv_w4_kernel(const GemvParams p) {
         else acc += sw[b];
       }
       if (P.bias) acc += __half2float(P.bias[row]);
-      P.y[(size_t)b * P.N + row] = __float2half_rn(acc);
+      const __half h = __float2half_rn(acc);
+      if (p.nranks == 0) {
+        P.y[(size_t)b * P.N + row] = h;
+      } else {
+        for (int pr = 0; pr < p.nranks; ++pr) p.y_peer[pr][S.part][(size_t)b * p.y_ld + row] = h;   // NVLink stores
+      }
+    }
+  }
+  if (p.nranks > 0) {
+    // publish: all of this CTA's peer stores are visible system-wide, then count the CTA; the last one signals
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned old = atomicAdd(p.local_count, 1u);
+      if (old == gridDim.x - 1) {
+        *p.local_count = 0u;                         // ready for the next step
+        __threadfence_system();
+        for (int pr = 0; pr < p.nranks; ++pr)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.done_peer[pr]) : "memory");
+      }
     }
   }
   stamp(p, 5);
@@ -800,6 +839,7 @@ static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_
     int q_hi = total_q;
     int grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
     if ((long)grid * q_per_cta_max < (long)(q_hi - q_lo)) q_hi = q_lo + grid * q_per_cta_max;
+    if (prm.nranks > 0 && (q_lo != 0 || q_hi != total_q)) return QEFT_E_UNSUPPORTED;   // the fused gather signals once per launch
     prm.q_lo = q_lo; prm.q_hi = q_hi;
     grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
     const int qmax = cdiv(q_hi - q_lo, grid);
@@ -832,9 +872,8 @@ static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_
 
 using namespace qeft;
 
-extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,
-                                  const int32_t* x_gather, int m, int K, int r, int G, unsigned flags,
-                                  qeft_stream_t stream) {
+static int gemv_entry(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout, const int32_t* x_gather,
+                      int m, int K, int r, int G, unsigned flags, const qeft_gather_t* gat, qeft_stream_t stream) {
   if (!x || !parts) return QEFT_E_NULL;
   if (nparts < 1 || nparts > QEFT_GEMV_MAX_PARTS) return QEFT_E_SHAPE;
   if (m < 1 || m > 8) return QEFT_E_BATCH;
@@ -848,7 +887,7 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
   int total_q = 0;
   for (int i = 0; i < nparts; ++i) {
     const qeft_gemv_part_t& q = parts[i];
-    if (!q.qweight || !q.scales || !q.scaled_zeros || !q.y) return QEFT_E_NULL;
+    if (!q.qweight || !q.scales || !q.scaled_zeros || (!q.y && !gat)) return QEFT_E_NULL;
     if (r > 0 && !q.oweight) return QEFT_E_NULL;
     if (q.N <= 0 || q.N % 8 != 0) return QEFT_E_SHAPE;
     if (!check_align16(q.qweight) || !check_align16(q.scales) || !check_align16(q.scaled_zeros) ||
@@ -875,7 +914,23 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
   prm.nchunks = (K - r) / 32;
   prm.nku = cdiv(prm.nsteps, 2);
   prm.nou = cdiv(r, 64);
-  prm.xstride = 128 * prm.nsteps + 32;   // the int4 steps' columns (dead columns of the last step staged as zeros)
+  prm.xstride = 128 * prm.nsteps + 32;
+  if (gat) {
+    if (gat->nranks < 1 || gat->nranks > QEFT_MAX_RANKS || !gat->local_count || !gat->epoch) return QEFT_E_SHAPE;
+    prm.nranks = gat->nranks;
+    prm.y_ld = gat->y_ld;
+    for (int pr = 0; pr < gat->nranks; ++pr) {
+      if (!gat->done_peer[pr]) return QEFT_E_NULL;
+      prm.done_peer[pr] = gat->done_peer[pr];
+      for (int i = 0; i < nparts; ++i) {
+        if (!gat->y_peer[pr][i]) return QEFT_E_NULL;
+        prm.y_peer[pr][i] = static_cast<__half*>(gat->y_peer[pr][i]);
+      }
+    }
+    prm.local_count = gat->local_count;
+    prm.wait_flag = gat->wait_flag;
+    prm.epoch = gat->epoch;
+  }   // the int4 steps' columns (dead columns of the last step staged as zeros)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool stage = x_gather != nullptr || (size_t)m * (size_t)(K + 136) * 2 <= kStageXMaxBytes;
   // batch 1-2 with staged x: the int8 tensor path (half the MMAs, 16 instead of 40 unpack instructions per step)
@@ -883,6 +938,19 @@ extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, 
   const size_t i8_bytes = (size_t)prm.nsteps * 3 * m * 144 + (size_t)m * r * 2;
   if (stage && m <= 2 && i8_env != 0 && i8_bytes <= kStageXMaxBytes) return launch_gemv<true, true>(prm, total_q, flags, st);
   return stage ? launch_gemv<true, false>(prm, total_q, flags, st) : launch_gemv<false, false>(prm, total_q, flags, st);
+}
+
+extern "C" int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,
+                                  const int32_t* x_gather, int m, int K, int r, int G, unsigned flags,
+                                  qeft_stream_t stream) {
+  return gemv_entry(x, parts, nparts, ow_layout, x_gather, m, K, r, G, flags, nullptr, stream);
+}
+
+extern "C" int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,
+                                         const int32_t* x_gather, int m, int K, int r, int G, unsigned flags,
+                                         const qeft_gather_t* gather, qeft_stream_t stream) {
+  if (!gather) return QEFT_E_NULL;
+  return gemv_entry(x, parts, nparts, ow_layout, x_gather, m, K, r, G, flags, gather, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int qeft_gemv_debug_stamps(unsigned long long* host_out, int nslots) {

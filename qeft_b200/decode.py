@@ -84,6 +84,50 @@ class PackedDecoderStack:
         self.grp_full = [[torch.empty((self.world, b.shape[1]), dtype=torch.float16, device=self.device) for b in gl]
                          for gl in self.grp_local]
 
+    def enable_fused_gather(self, process_group):
+        """Column-sharded execution WITHOUT a collective call: the GEMV epilogue stores each rank's slice into every
+        rank's gathered buffer (symmetric memory, peer pointers over NVLink) and signals per-launch arrival counters;
+        a launch waits for the counter of the launch before it (the chain's data dependency).  One symmetric
+        allocation holds the counters and all gathered outputs."""
+        import torch.distributed._symmetric_memory as symm_mem
+        assert self.batch == 1 and self.fused
+        m, P = self.batch, self.world
+        widths = [[b.shape[1] for b in gl] for gl in self.grp_local]          # local width of every launch group
+        nlaunch = sum(len(w) for w in widths)
+        flag_bytes = ((nlaunch * 4 + 255) // 256) * 256
+        total = flag_bytes + sum(2 * m * P * w for ws in widths for w in ws)
+        buf = symm_mem.empty((total,), dtype=torch.uint8, device=self.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, process_group)
+        self._symm = (buf, hdl)
+        self.epoch = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self.local_counts = torch.zeros((nlaunch,), dtype=torch.int32, device=self.device)
+        self.fused_gather = []
+        off, li_flat, prev_flag = flag_bytes, 0, None
+        for li, ws in enumerate(widths):
+            row = []
+            for gi, w in enumerate(ws):
+                g = _lib.Gather()
+                g.nranks, g.y_ld = P, P * w
+                names = self.groups[gi]
+                for pr in range(P):
+                    base = hdl.buffer_ptrs[pr] + off + 2 * self.rank * w      # my column slot in rank pr's buffer
+                    col = 0
+                    for i, n in enumerate(names):
+                        g.y_peer[pr][i] = base + 2 * col
+                        col += self.blocks[li][n]["N"]
+                    g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * li_flat
+                g.local_count = self.local_counts.data_ptr() + 4 * li_flat
+                g.wait_flag = prev_flag
+                g.epoch = self.epoch.data_ptr()
+                prev_flag = buf.data_ptr() + 4 * li_flat
+                row.append((g, buf[off:off + 2 * m * P * w].view(torch.float16).view(m, P * w)))
+                off += 2 * m * P * w
+                li_flat += 1
+            self.fused_gather.append(row)
+        hdl.barrier()
+        self.pg = None
+
     def _gather(self, li, gi):
         if self.pg is not None:
             import torch.distributed as dist
@@ -110,10 +154,17 @@ class PackedDecoderStack:
     def step_eager(self):
         m, r, G, h, f = self.batch, self.r, self.G, self.h, self.f
         lay = _lib.OW_INTERLEAVED
+        fg = getattr(self, "fused_gather", None)
+        if fg is not None:
+            self.epoch.add_(1)                     # one step: every arrival counter advances by `world`
         for li, (blk, out) in enumerate(zip(self.blocks, self.out)):
             for gi, names in enumerate(self.groups):
                 x = self.x_f if names[0] == "down" else self.x_h
                 gather = blk["o"].get("reorder_ids32") if names[0] == "o" else None
+                if fg is not None:
+                    qeft_cuda.gemv_w4_multi_gather(x, [self._part(blk[n], None) for n in names], m, x.shape[-1], r, G,
+                                                   fg[li][gi][0], ow_layout=lay, x_gather=gather, pdl=self.pdl)
+                    continue
                 if self.fused:
                     qeft_cuda.gemv_w4_multi(x, [self._part(blk[n], out[n]) for n in names], m, x.shape[-1], r, G,
                                             ow_layout=lay, x_gather=gather, pdl=self.pdl)

@@ -111,6 +111,21 @@ def gemv_w4_multi(x, parts: Sequence[dict], m, k, r, group_size, *, ow_layout, x
     return outs
 
 
+def gemv_w4_multi_gather(x, parts: Sequence[dict], m, k, r, group_size, gather, *, ow_layout, x_gather=None, pdl=None):
+    """Column-sharded decode: like :func:`gemv_w4_multi`, but every part's result is stored by the kernel into
+    every rank's gathered buffer (``gather``: a prepared ``_lib.Gather``; see include/qeft_b200.h).  Returns None."""
+    _need_cuda(x)
+    x = _f16(x, "in_feats")
+    arr = (_lib.GemvPart * len(parts))()
+    for i, p in enumerate(parts):
+        arr[i] = _lib.GemvPart(_ptr(p["qweight"]), _ptr(p["scales"]), _ptr(p["scaled_zeros"]),
+                               _ptr(p.get("oweight")), _ptr(p.get("bias")), None, p["N"])
+    with torch.cuda.device(x.device):
+        st = _lib.load().qeft_gemv_w4_multi_gather(_ptr(x), arr, len(parts), ow_layout, _ptr(x_gather), m, k, r,
+                                                   group_size, _flags(pdl), C.byref(gather), _stream(x))
+    _lib.check(st, "qeft_gemv_w4_multi_gather")
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float16:
         return _lib.DT_F16
