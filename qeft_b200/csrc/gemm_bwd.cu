@@ -123,53 +123,70 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
     // destination: 64-feature chunk kc/2 (8 KB apart), row nl, 16-byte chunks (kc%2)*4 + i, XOR-swizzled with nl%8
     const uint32_t dst_row = (uint32_t)((kc >> 1) * (kDxBK * 128) + nl * 128);
     const int sw = nl & 7;
-    auto load_q = [&](int kb, uint4& q, unsigned short& sh, unsigned short& zh) {
+    // register prefetch ring, kPF k-blocks deep (weights and scales come from L2, ~700 cycles away)
+    constexpr int kPF = 4;
+    auto load_q = [&](int kb, uint4& q, uint32_t& sz) {
       const int n = kb * kDxBK + nl;
-      if (outl) return;
       q = ldg_nc_v4(p.qw + (size_t)(n >> 2) * (size_t)(2 * p.K) + (size_t)((n & 3) * 32) + in_row);
-      sh = ldg_nc_u16(p.scales + (size_t)grp * p.N + n);
-      zh = ldg_nc_u16(p.szeros + (size_t)grp * p.N + n);
+      sz = (uint32_t)ldg_nc_u16(p.scales + (size_t)grp * p.N + n) | ((uint32_t)ldg_nc_u16(p.szeros + (size_t)grp * p.N + n) << 16);
     };
-    uint4 q = make_uint4(0, 0, 0, 0), qn = q;
-    unsigned short sh = 0, zh = 0, shn = 0, zhn = 0;
-    if (live) load_q(0, q, sh, zh);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kDxStages, use = kb / kDxStages;
-      if (live && kb + 1 < nkb) load_q(kb + 1, qn, shn, zhn);
-      uint32_t v[16];
-      if (!live) {
+    auto load_o = [&](int kb, uint4 (&o)[4]) {
+      const __half* src = p.ow + (size_t)(kb * kDxBK + nl) * p.r + (kf - (p.K - p.r));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0u;
-      } else if (outl) {
-        const __half* src = p.ow + (size_t)(kb * kDxBK + nl) * p.r + (kf - (p.K - p.r));
+      for (int i = 0; i < 4; ++i) o[i] = ldg_nc_v4(src + 8 * i);
+    };
+    uint4 ring[kPF];
+    uint32_t rsz[kPF];
+    uint4 onext[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 t4 = ldg_nc_v4(src + 8 * i);
-          v[4 * i + 0] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
-        }
-      } else {
-        const uint32_t s2 = (uint32_t)sh | ((uint32_t)sh << 16), z2 = (uint32_t)zh | ((uint32_t)zh << 16);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    for (int i = 0; i < kPF; ++i) {
+      ring[i] = make_uint4(0, 0, 0, 0); rsz[i] = 0;
+      if (live && !outl && i < nkb) load_q(i, ring[i], rsz[i]);
+    }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hq[4];
-          unpack_word_to_half2(w[c], hq);                        // pairs k = 2 c + 8 j (+1), exact 0..15
+    for (int i = 0; i < 4; ++i) onext[i] = make_uint4(0, 0, 0, 0);
+    if (outl) load_o(0, onext);
+    for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[c + 4 * j] = hfma2_u32(hq[j], s2, z2);     // w = fma(q, s, sz)
+      for (int u = 0; u < kPF; ++u) {
+        const int kb = kb0 + u;
+        if (kb < nkb) {
+          const int s = kb % kDxStages, use = kb / kDxStages;
+          uint32_t v[16];
+          if (!live) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          } else if (outl) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[4 * i + 0] = onext[i].x; v[4 * i + 1] = onext[i].y; v[4 * i + 2] = onext[i].z; v[4 * i + 3] = onext[i].w; }
+            if (kb + 1 < nkb) load_o(kb + 1, onext);
+          } else {
+            const uint4 q = ring[u];
+            const uint32_t sz = rsz[u];
+            if (kb + kPF < nkb) load_q(kb + kPF, ring[u], rsz[u]);
+            const uint32_t s2 = (sz & 0xffffu) | (sz << 16), z2 = (sz >> 16) | (sz & 0xffff0000u);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t hq[4];
+              unpack_word_to_half2(w[c], hq);                        // pairs k = 2 c + 8 j (+1), exact 0..15
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[c + 4 * j] = hfma2_u32(hq[j], s2, z2);     // w = fma(q, s, sz)
+            }
+          }
+          if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
+          const uint32_t base = st0 + s * kDxStageBytes + kDxABytes + dst_row;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = base + (uint32_t)(((((kc & 1) << 2) + i) ^ sw) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]),
+                         "r"(v[4 * i + 3]) : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full(s));
         }
       }
-      if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
-      const uint32_t base = st0 + s * kDxStageBytes + kDxABytes + dst_row;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t a = base + (uint32_t)(((((kc & 1) << 2) + i) ^ sw) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]),
-                     "r"(v[4 * i + 3]) : "memory");
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full(s));
-      q = qn; sh = shn; zh = zhn;
     }
 
     // ---- epilogue: lanes = tokens, columns = features -> fp16, 16-byte stores ----
