@@ -66,6 +66,7 @@ struct GemvParams {
   int q_lo, q_hi;         // window of launch-wide qweight rows this launch covers
   int max_tiles;          // upper bound of tiles per CTA (sizes the partial-sum slices)
   unsigned long long* stamps;   // debug (QEFT_GEMV_STAMPS): [launch slot][8] globaltimer values of CTA 0, or null
+  unsigned long long* cta_stamps;   // debug: [512 CTAs][4] start / waited / staged / stored of this launch, or null
   // fused all-gather (column-sharded decode): results go to every rank's gathered buffer
   int nranks;                   // 0: plain launch (part.y)
   int y_ld;
@@ -123,10 +124,14 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 __device__ __forceinline__ void stamp(const GemvParams& p, int i) {
-  if (p.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (p.stamps && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.stamps[i] = t;
+    if (blockIdx.x == 0) p.stamps[i] = t;
+    if (p.cta_stamps && blockIdx.x < 512 && (i == 0 || i == 2 || i == 3 || i == 5)) {
+      const int j = i == 0 ? 0 : (i == 2 ? 1 : (i == 3 ? 2 : 3));
+      p.cta_stamps[blockIdx.x * 4 + j] = t;
+    }
   }
 }
 
@@ -757,6 +762,11 @@ gemv_w4_kernel(const GemvParams p) {
     }
   }
   stamp(p, 5);
+  if (p.stamps && threadIdx.x == 0) {          // debug: the last CTA's finish time
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(p.stamps + 6, t);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -815,9 +825,11 @@ template <bool XS, bool I8>
 static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_t stream) {
   static const int stamps_env = env_int("QEFT_GEMV_STAMPS", 0);
   if (stamps_env && !g_stamps) {
-    if (cudaMalloc(&g_stamps, 4096 * 8 * sizeof(unsigned long long)) != cudaSuccess) g_stamps = nullptr;
-    else cudaMemset(g_stamps, 0, 4096 * 8 * sizeof(unsigned long long));
+    const size_t bytes = (4096 * 8 + 64 * 512 * 4) * sizeof(unsigned long long);
+    if (cudaMalloc(&g_stamps, bytes) != cudaSuccess) g_stamps = nullptr;
+    else cudaMemset(g_stamps, 0, bytes);
   }
+  prm.cta_stamps = g_stamps ? g_stamps + 4096 * 8 + (g_stamp_launch % 64) * 512 * 4 : nullptr;
   prm.stamps = g_stamps ? g_stamps + (g_stamp_launch++ % 4096) * 8 : nullptr;
   static const int depth_env = env_int("QEFT_GEMV_DEPTH", 0);
   static const int cps_env = env_int("QEFT_GEMV_CTAS_PER_SM", 0);
@@ -956,6 +968,14 @@ extern "C" int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* 
 extern "C" __attribute__((visibility("default"))) int qeft_gemv_debug_stamps(unsigned long long* host_out, int nslots) {
   if (!g_stamps || !host_out || nslots <= 0 || nslots > 4096) return QEFT_E_NULL;
   cudaError_t e = cudaMemcpy(host_out, g_stamps, (size_t)nslots * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? QEFT_OK : (int)e;
+}
+
+// per-CTA stamps of launch slot `slot` (launch number % 64): host_out[512][4]
+extern "C" __attribute__((visibility("default"))) int qeft_gemv_debug_cta_stamps(unsigned long long* host_out, int slot) {
+  if (!g_stamps || !host_out || slot < 0 || slot >= 64) return QEFT_E_NULL;
+  cudaError_t e = cudaMemcpy(host_out, g_stamps + 4096 * 8 + (size_t)slot * 512 * 4, 512 * 4 * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost);
   return e == cudaSuccess ? QEFT_OK : (int)e;
 }
 

@@ -49,8 +49,28 @@ total = 3 * args.n
 buf = (C.c_ulonglong * (total * 8))()
 assert lib.qeft_gemv_debug_stamps(buf, total) == 0
 # the graph replay re-uses the slots of the captured launches (slots n .. 2n-1): replayed kernels carry those pointers
-rows = [[buf[i * 8 + j] for j in range(6)] for i in range(args.n, 2 * args.n)]
+rows = [[buf[i * 8 + j] for j in range(7)] for i in range(args.n, 2 * args.n)]
 t0 = rows[0][0]
-print("launch  start  filled  waited  staged  looped  stored   (us, relative to the first launch's start)")
+print("launch  start  filled  waited  staged  looped  stored  last-CTA-stored (us, relative to the first launch's start; the last column accumulates over replays)")
 for i, r in enumerate(rows):
     print(i, " ".join(f"{(v - t0) / 1e3:8.2f}" for v in r))
+
+# per-CTA view of one mid-chain launch (slot = launch number % 64)
+import numpy as np
+slot = (args.n + args.n // 2) % 64
+cb = (C.c_ulonglong * (512 * 4))()
+lib.qeft_gemv_debug_cta_stamps.restype = C.c_int
+if lib.qeft_gemv_debug_cta_stamps(cb, slot) == 0:
+    a = np.array(cb[:], dtype=np.int64).reshape(512, 4)
+    a = a[a[:, 0] > 0]
+    base = a[:, 0].min()
+    rel = (a - base) / 1e3
+    names = ["start", "waited", "staged", "stored"]
+    print(f"per-CTA stamps of launch {args.n // 2} ({len(a)} CTAs), us relative to the earliest start:")
+    for j, nm in enumerate(names):
+        col = rel[:, j]
+        print(f"  {nm:7s} min {col.min():7.2f}  p50 {np.median(col):7.2f}  p90 {np.percentile(col, 90):7.2f}  max {col.max():7.2f}")
+    d = rel[:, 3] - rel[:, 2]
+    print(f"  staged->stored per CTA: min {d.min():.2f} p50 {np.median(d):.2f} max {d.max():.2f}")
+    d = rel[:, 2] - rel[:, 1]
+    print(f"  waited->staged per CTA: min {d.min():.2f} p50 {np.median(d):.2f} max {d.max():.2f}")
