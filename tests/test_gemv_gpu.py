@@ -63,6 +63,22 @@ def test_gemv_llama7b_ffn_shapes(shape):
     assert rel_err(got, want) <= REL_TOL
 
 
+@pytest.mark.parametrize("N,K,r,m", [
+    (12288, 256, 64, 8),     # more rows than one launch's partial-sum slices hold at m = 8: split into row windows
+    (64, 8192, 128, 8),      # x too large to stage in shared memory: activations read through L1/L2
+    (72, 1024, 288, 2),      # r > 256 (three outlier units per tile), N % 16 == 8, int8 path
+    (256, 640, 96, 5),       # r % 64 != 0, K - r not a multiple of 128 (dead chunks in the last step)
+])
+def test_gemv_uncommon_shapes(N, K, r, m):
+    from qeft_b200 import _lib
+    L = oracle.synth_layer(N, K, r=r, G=128, seed=N + m, bias=True)
+    x = np.random.default_rng(m).standard_normal((m, K)).astype(np.float16)
+    want = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], L["bias"])
+    for layout in (_lib.OW_INTERLEAVED, _lib.OW_PLAIN):
+        got = run_gemv(L, x, layout, bias=L["bias"])
+        assert rel_err(got, want) <= REL_TOL, (layout, rel_err(got, want))
+
+
 def test_gemv_o_proj_gather_fused():
     from qeft_b200 import _lib
     N, K, r = 256, 512, 128
