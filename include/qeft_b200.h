@@ -131,7 +131,10 @@ QEFT_API int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* pa
  * Replaces  gemm_4bit (qeft/kernel/quantization_new/gemm/gemm_cuda.cu:929-1033)  PLUS the separate
  * `y += F.linear(x[..., -r:], oweight)` and `y + bias` of qeft/qlinear.py:264-268 in one kernel.
  * oweight is the PLAIN [N, r] tensor (may be NULL when r == 0).  GEMV semantics for the outlier
- * columns (the dead int4 columns are skipped).  Requires N % 128 == 0, K % 64 == 0, r % 64 == 0, G == 128.
+ * columns (the dead int4 columns are skipped).  Requires N % 128 == 0, K % 64 == 0, r % 64 == 0, G % 64 == 0.
+ * dtype: QEFT_DT_F16 (x, oweight, y fp16; w = fma.rn.f16(q, s, sz) like the reference) or QEFT_DT_BF16 (x, oweight,
+ * y bf16; the int4 columns are dequantised in fp32 with one rounding to bf16).  scales, scaled_zeros and bias are
+ * always the checkpoint's fp16.  The same holds for qeft_gemm_w4_dx and qeft_dow.
  */
 QEFT_API int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
                  const void* oweight, const void* bias, void* y, int M, int N, int K, int r, int G,

@@ -78,6 +78,15 @@ __device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c
   return d;
 }
 
+// bf16 flavour of the dequant: {q0, q1} exact fp16 integers, s / sz the group's fp16 scale and scaled zero as fp32.
+// w = fma(q, s, sz) in fp32, ONE rounding to bf16 (round to nearest even), packed {lo, hi}.
+__device__ __forceinline__ uint32_t dequant_pair_bf16(uint32_t q2, float s, float sz) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&q2);
+  const float2 q = __half22float2(h);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(fmaf(q.x, s, sz), fmaf(q.y, s, sz));
+  return *reinterpret_cast<const uint32_t*>(&b);
+}
+
 __device__ __forceinline__ float2 half2_bits_to_float2(uint32_t v) {
   __half2 h = *reinterpret_cast<__half2*>(&v);
   return __half22float2(h);

@@ -43,6 +43,7 @@ struct DxParams {
   int M, N, K, r, G;
 };
 
+template <bool BF16>
 __global__ void __launch_bounds__(kDxThreads, 1)
 gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,7 +92,7 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kDxBF, false, true);
+      constexpr uint32_t idesc = make_idesc_f16(kDxBF, false, true) | (BF16 ? ((1u << 7) | (1u << 10)) : 0u);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kDxStages;
         mbar_wait(full(s), (uint32_t)((kb / kDxStages) & 1));
@@ -171,7 +172,10 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
               uint32_t hq[4];
               unpack_word_to_half2(w[c], hq);                        // pairs k = 2 c + 8 j (+1), exact 0..15
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[c + 4 * j] = hfma2_u32(hq[j], s2, z2);     // w = fma(q, s, sz)
+              for (int j = 0; j < 4; ++j)
+                v[c + 4 * j] = BF16 ? dequant_pair_bf16(hq[j], __half2float(__ushort_as_half((unsigned short)(sz & 0xffffu))),
+                                                        __half2float(__ushort_as_half((unsigned short)(sz >> 16))))
+                                    : hfma2_u32(hq[j], s2, z2);                        // w = fma(q, s, sz)
             }
           }
           if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
@@ -207,11 +211,18 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 o;
-            __half2 h;
-            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 0]), __uint_as_float(acc[8 * i + 1])); o.x = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])); o.y = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])); o.z = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])); o.w = *reinterpret_cast<uint32_t*>(&h);
+            auto pack2 = [](uint32_t a, uint32_t b) {
+              if (BF16) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b));
+                return *reinterpret_cast<const uint32_t*>(&v);
+              }
+              const __half2 v = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
+              return *reinterpret_cast<const uint32_t*>(&v);
+            };
+            o.x = pack2(acc[8 * i + 0], acc[8 * i + 1]);
+            o.y = pack2(acc[8 * i + 2], acc[8 * i + 3]);
+            o.z = pack2(acc[8 * i + 4], acc[8 * i + 5]);
+            o.w = pack2(acc[8 * i + 6], acc[8 * i + 7]);
             *reinterpret_cast<uint4*>(dst + 8 * i) = o;
           }
         }
@@ -236,7 +247,7 @@ constexpr int kDwThreads = 192;           // warp 0 TMA, warp 1 MMA (+ TMEM allo
 
 struct DowParams {
   float* dow;              // [N, r]
-  int M, N, r, accumulate;
+  int M, N, r, accumulate, bf16;
 };
 
 // one CTA: 128 output features n0..n0+127 x all r (<= 256) outlier columns, contraction over all M tokens
@@ -288,7 +299,7 @@ dow_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.r, true, true);
+      const uint32_t idesc = make_idesc_f16(p.r, true, true) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kDwStages;
         mbar_wait(full(s), (uint32_t)((kb / kDwStages) & 1));
@@ -357,7 +368,7 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
                                const void* oweight, void* dx, int M, int N, int K, int r, int G, int dtype,
                                unsigned flags, qeft_stream_t stream) {
   if (!dy || !qweight || !scales || !scaled_zeros || !dx) return QEFT_E_NULL;
-  if (dtype != QEFT_DT_F16) return dtype == QEFT_DT_BF16 ? QEFT_E_UNSUPPORTED : QEFT_E_DTYPE;
+  if (dtype != QEFT_DT_F16 && dtype != QEFT_DT_BF16) return QEFT_E_DTYPE;
   if (G == -1) G = K;
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 64 != 0 || G <= 0 || G % 64 != 0 || K % G != 0) return QEFT_E_SHAPE;
   if (r < 0 || r % 64 != 0 || r >= K) return QEFT_E_SHAPE;
@@ -374,8 +385,9 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
   prm.dx = static_cast<__half*>(dx);
   prm.M = M; prm.N = N; prm.K = K; prm.r = r; prm.G = G;
   const size_t smem = (size_t)kDxStages * kDxStageBytes + 1024;
-  static bool done[64] = {};
-  st = set_smem_once(gemm_w4_dx_kernel, smem, done);
+  static bool done[2][64] = {};
+  const bool bf = dtype == QEFT_DT_BF16;
+  st = bf ? set_smem_once(gemm_w4_dx_kernel<true>, smem, done[1]) : set_smem_once(gemm_w4_dx_kernel<false>, smem, done[0]);
   if (st != QEFT_OK) return st;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)cdiv(M, 128 * kDxTB), (unsigned)cdiv(K, kDxBF));
@@ -387,7 +399,8 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (flags & QEFT_F_PDL) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel, dymap, prm);
+  cudaError_t e = bf ? cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel<true>, dymap, prm)
+                     : cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel<false>, dymap, prm);
   if (e != cudaSuccess) return (int)e;
   count_launch();
   return QEFT_OK;
@@ -396,7 +409,7 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
 extern "C" int qeft_dow(const void* dy, const void* x, float* dow, int M, int N, int K, int r, int dtype, int accumulate,
                         unsigned flags, qeft_stream_t stream) {
   if (!dy || !x || !dow) return QEFT_E_NULL;
-  if (dtype != QEFT_DT_F16) return dtype == QEFT_DT_BF16 ? QEFT_E_UNSUPPORTED : QEFT_E_DTYPE;
+  if (dtype != QEFT_DT_F16 && dtype != QEFT_DT_BF16) return QEFT_E_DTYPE;
   // x is the [M, K] activation (the last r columns are used) or, with K == r, the compact [M, r] copy
   if (M <= 0 || N <= 0 || N % 128 != 0 || r <= 0 || r % 64 != 0 || r > 256 || K < r || K % 8 != 0) return QEFT_E_SHAPE;
   if (!check_align16(dy) || !check_align16(x) || !check_align16(dow)) return QEFT_E_ALIGN;
@@ -407,7 +420,7 @@ extern "C" int qeft_dow(const void* dy, const void* x, float* dow, int M, int N,
   st = make_tmap_f16_2d_pitched(&xomap, static_cast<const __half*>(x) + (K - r), (uint64_t)M, (uint64_t)r, (uint64_t)K, kDwBK);
   if (st != QEFT_OK) return st;
   DowParams prm;
-  prm.dow = dow; prm.M = M; prm.N = N; prm.r = r; prm.accumulate = accumulate;
+  prm.dow = dow; prm.M = M; prm.N = N; prm.r = r; prm.accumulate = accumulate; prm.bf16 = dtype == QEFT_DT_BF16;
   const size_t smem = (size_t)kDwStages * (2 * kDwBK * 128 + (size_t)(r / 64) * kDwBK * 128) + 1024;
   static bool done[64] = {};
   st = set_smem_once(dow_kernel, 200 * 1024, done);

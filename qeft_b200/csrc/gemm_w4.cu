@@ -50,7 +50,9 @@ struct GemmCfg {
   static constexpr int kStages = kXStagesMax < kAStagesMax ? kXStagesMax : kAStagesMax;
   static constexpr int kXStages = kStages, kAStages = kStages;
   static constexpr int kSets = kDequantWarps / (4 * NRB);    // sets of dequant warps that alternate ring stages
-  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // kind::f16 instruction descriptor: D = F32 (bit 4), A / B format at bits 7 / 10 (0 = F16, 1 = BF16), K-major, N, M = 128
+  static constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static constexpr uint32_t kIdescBF16 = kIdescF16 | (1u << 7) | (1u << 10);
   static_assert(kTmemA0 + kAStages * kAStageCols <= kTmemCols, "TMEM budget");
   static_assert(kSets >= 1 && kSets * 4 * NRB == kDequantWarps, "every dequant warp belongs to exactly one set");
 };
@@ -84,14 +86,14 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor (Cfg::kIdesc): D = F32, A = B = F16, both K-major, M = 128, N = BN
 // MC: clusters of two CTAs (adjacent feature blocks, same tokens) share every activation tile: each CTA loads one
 // half with a multicast TMA, both receive the whole tile -- halves the L2 -> SM activation traffic.
-template <int NRB, int BN, bool MC>
+template <int NRB, int BN, bool MC, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   using Cfg = GemmCfg<NRB, BN>;
   constexpr int kBM = Cfg::kBM, kBN = Cfg::kBN, kXStages = Cfg::kXStages, kAStages = Cfg::kAStages;
   constexpr int kXStageBytes = Cfg::kXStageBytes, kTmemA0 = Cfg::kTmemA0, kDequantSets = Cfg::kSets;
   constexpr int kKPS = Cfg::kKPS, kXTileBytes = Cfg::kXTileBytes;
-  constexpr uint32_t kIdesc = Cfg::kIdesc;
+  constexpr uint32_t kIdesc = BF16 ? Cfg::kIdescBF16 : Cfg::kIdescF16;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kXStages + 1];
   __shared__ uint32_t s_tmem_base;
@@ -270,7 +272,10 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
                 uint32_t hq[4];
                 unpack_word_to_half2(w[4 * h + c], hq);          // pairs k = 32 h + 2 c + 8 j (+1), exact 0..15
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[16 * h + c + 4 * j] = hfma2_u32(hq[j], s2, z2);   // w = fma(q, s, sz)
+                for (int j = 0; j < 4; ++j)
+                  v[16 * h + c + 4 * j] = BF16 ? dequant_pair_bf16(hq[j], __half2float(__ushort_as_half((unsigned short)(s2 & 0xffffu))),
+                                                                   __half2float(__ushort_as_half((unsigned short)(z2 & 0xffffu))))
+                                               : hfma2_u32(hq[j], s2, z2);                      // w = fma(q, s, sz)
               }
           } else {
             // outlier k-block: fp16 columns, copied unchanged
@@ -298,7 +303,11 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         tmem_ld32(lane_taddr + (uint32_t)(kBN * rb + 32 * tc), acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stage[i * 32 + lane] = __float2half_rn(__uint_as_float(acc[i]) + bias);
+        for (int i = 0; i < 32; ++i) {
+          const float val = __uint_as_float(acc[i]) + bias;
+          if (BF16) reinterpret_cast<__nv_bfloat16*>(stage)[i * 32 + lane] = __float2bfloat16_rn(val);
+          else stage[i * 32 + lane] = __float2half_rn(val);
+        }
         __syncwarp();
         // 32 rows (tokens) of 64 bytes: 4 lanes per row, 8 rows per pass
 #pragma unroll
@@ -361,13 +370,13 @@ int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
   return make_tmap_f16_2d_pitched(map, base, rows, cols, cols, box_rows);
 }
 
-template <int NRB, int BN, bool MC>
+template <int NRB, int BN, bool MC, bool BF16>
 static int launch_gemm(const void* x, const GemmParams& prm, unsigned flags, cudaStream_t stream) {
   using Cfg = GemmCfg<NRB, BN>;
   CUtensorMap xmap;
   int st = make_tmap_f16_2d(&xmap, x, (uint64_t)prm.M, (uint64_t)prm.K, MC ? BN / 2 : BN);
   if (st != QEFT_OK) return st;
-  auto kern = gemm_w4_kernel<NRB, BN, MC>;
+  auto kern = gemm_w4_kernel<NRB, BN, MC, BF16>;
   const size_t smem = (size_t)Cfg::kXStages * Cfg::kXStageBytes + 1024;
   static bool attr_set[64] = {};
   int dev = 0;
@@ -410,7 +419,7 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
                             const void* oweight, const void* bias, void* y, int M, int N, int K, int r, int G,
                             int dtype, unsigned flags, qeft_stream_t stream) {
   if (!x || !qweight || !scales || !scaled_zeros || !y) return QEFT_E_NULL;
-  if (dtype != QEFT_DT_F16) return dtype == QEFT_DT_BF16 ? QEFT_E_UNSUPPORTED : QEFT_E_DTYPE;
+  if (dtype != QEFT_DT_F16 && dtype != QEFT_DT_BF16) return QEFT_E_DTYPE;
   if (G == -1) G = K;
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 64 != 0 || G <= 0 || G % 64 != 0 || K % G != 0) return QEFT_E_SHAPE;
   if (r < 0 || r % 64 != 0 || r >= K) return QEFT_E_SHAPE;
@@ -432,7 +441,10 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   // QEFT_GEMM_CFG=3: 2-CTA clusters multicast every activation tile (halves the L2 reads; measured 2-5 % slower than
   // the plain launch on B200 because L2 bandwidth is not the limiter at these sizes, so it is not the default)
-  if (cfg_env == 3 && N % 256 == 0) return launch_gemm<1, 256, true>(x, prm, flags, cs);
-  return launch_gemm<1, 256, false>(x, prm, flags, cs);
+  // bf16: x, oweight and y are bf16 (bias, scales, scaled zeros stay fp16 as in the checkpoint); the int4 columns are
+  // dequantised in fp32 with one rounding to bf16
+  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs);
+  if (cfg_env == 3 && N % 256 == 0) return launch_gemm<1, 256, true, false>(x, prm, flags, cs);
+  return launch_gemm<1, 256, false, false>(x, prm, flags, cs);
 }
 

@@ -99,3 +99,39 @@ def test_gemm_llama7b_shapes_m2048_properties(shape):
     y3 = qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, pdl=False)
     torch.cuda.synchronize()
     assert torch.equal(y, y3)
+
+
+def _bf16_round(a):
+    """fp32 -> bf16 (round to nearest even) -> fp32, in numpy."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("M,N,K,r", [(96, 256, 512, 128), (300, 384, 1024, 64)])
+def test_gemm_and_backward_bf16(M, N, K, r):
+    """bf16 activations / outputs (north_star tolerance 1e-2): int4 columns dequantised in fp32 with one rounding to
+    bf16, outlier columns and activations bf16, fp32 accumulation."""
+    from qeft_b200 import qeft_cuda
+    L = oracle.synth_layer(N, K, r=r, seed=M + r, bias=True)
+    rng = np.random.default_rng(M)
+    x = _bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    dy = _bf16_round(rng.standard_normal((M, N)).astype(np.float32))
+    q = oracle.unpack_intweight(L["qweight"]).astype(np.float64)
+    s = np.repeat(L["scales"].astype(np.float64).T, 128, axis=1)
+    z = np.repeat(L["scaled_zeros"].astype(np.float64).T, 128, axis=1)
+    W = _bf16_round((q * s + z).astype(np.float32)).astype(np.float64)       # fma in (at least) fp32, one rounding
+    ow = _bf16_round(L["oweight"].astype(np.float32))
+    W[:, K - r:] = ow
+    want_y = x.astype(np.float64) @ W.T + L["bias"].astype(np.float64)
+    want_dx = dy.astype(np.float64) @ W
+    want_dw = dy.astype(np.float64).T @ x[:, K - r:].astype(np.float64)
+    tb = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda().to(torch.bfloat16)  # noqa: E731  (exact: already bf16 values)
+    y = qeft_cuda.gemm_w4(tb(x), dev(L["qweight"]), dev(L["scales"]), dev(L["scaled_zeros"]), tb(ow), dev(L["bias"]), pdl=False)
+    dx = qeft_cuda.gemm_w4_dx(tb(dy), dev(L["qweight"]), dev(L["scales"]), dev(L["scaled_zeros"]), tb(ow), K, pdl=False)
+    dw = qeft_cuda.dow(tb(dy), tb(x), r)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.bfloat16 and dx.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert rel_err(y.float().cpu().numpy(), want_y) <= 1e-2
+    assert rel_err(dx.float().cpu().numpy(), want_dx) <= 1e-2
+    assert rel_err(dw.cpu().numpy(), want_dw) <= 1e-4
