@@ -231,6 +231,9 @@ gemv_w4_kernel(const GemvParams p) {
   const __half* pf_ow = nullptr;     // outlier source of this lane at column 0
   int pf_ownA = 0, pf_ownB = 0, pf_sc_ok = 0;
   size_t pf_sc_step = 0;             // halves between consecutive steps' scale rows (G = 128: N)
+  const uint8_t* pf_wb = nullptr;    // pf_w + one qweight row
+  const __half* pf_scl = nullptr;    // pf_sc + (lane / 4) steps (this lane's step of unit 0)
+  size_t pf_sc_step2 = 0;            // two steps
   auto pf_set_tile = [&](int tord) {
     int sg = 0;
 #pragma unroll
@@ -247,15 +250,28 @@ gemv_w4_kernel(const GemvParams p) {
     pf_sc = (which ? P.szeros : P.scales) + 16 * T + 8 * half8;
     pf_sc_ok = lane < 8 && (16 * T + 8 * half8) < P.N;
     pf_sc_step = (size_t)P.N;
+    pf_wb = pf_w + (size_t)(2 * K);
+    pf_scl = pf_sc + (size_t)(lane >> 2) * (size_t)P.N;
+    pf_sc_step2 = 2 * (size_t)P.N;
     if (inter)
       pf_ow = P.ow + (size_t)(8 * T + 4 * (g >> 2) + (g & 3)) * (size_t)(2 * r) + 8 * t;
     else
       pf_ow = P.ow + (size_t)(16 * T + ra) * (size_t)r + 8 * t;
   };
   // issue the copies of unit `su` of the cached tile into `slot` (predicated copies, no divergent branches)
+  const int pf_nfull = p.g128 == 1 ? (nchunks >> 3) : 0;     // units whose two steps are fully live (and G = 128)
   auto issue = [&](uint32_t slot, int su) {
     const uint32_t mine = slot + lane * 16;
-    if (su < nku) {
+    if (su < pf_nfull) {
+      // the common case: no liveness tests, no group arithmetic -- five predicated copies
+      const uint8_t* a = pf_w + (uint32_t)su * (uint32_t)(2 * kStepBytes);
+      const uint8_t* b = pf_wb + (uint32_t)su * (uint32_t)(2 * kStepBytes);
+      cp_async16_if(mine, a, pf_ownA);
+      cp_async16_if(mine + 1024, a + kStepBytes, pf_ownA);
+      cp_async16_if(mine + 512, b, pf_ownB);
+      cp_async16_if(mine + 1536, b + kStepBytes, pf_ownB);
+      cp_async16_if(slot + 2048 + lane * 16, pf_scl + (size_t)su * pf_sc_step2, pf_sc_ok);
+    } else if (su < nku) {
       const uint8_t* a = pf_w + (size_t)su * (2 * kStepBytes);
       const uint8_t* b = a + (size_t)(2 * K);
       const int c0 = 8 * su + t;                    // this lane's 32-column chunk of the unit's first step
