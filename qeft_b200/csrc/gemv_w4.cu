@@ -856,27 +856,36 @@ static int launch_gemv(GemvParams& prm, int total_q, unsigned flags, cudaStream_
   // the kernel is bound by instruction issue, not by bytes in flight: wide launches run two CTAs per SM (16 warps)
   // once every CTA still gets at least 8 qweight rows; narrow ones keep one CTA per SM so that the next launch's
   // CTA can be co-resident under programmatic dependent launch
-  const int cps = cps_env > 0 ? cps_env : (total_q >= 2 * 8 * num_sms() ? 2 : 1);
-  const int sms = num_sms() * cps;
+  const int cps_want = cps_env > 0 ? cps_env : (total_q >= 2 * 8 * num_sms() ? 2 : 1);
   // rows per launch: the partial-sum slices of a CTA must fit kPartMaxBytes
   const size_t tile_part = sizeof(float) * kWarps * 16 * (size_t)(I8 ? 4 * m : m);
   int tiles_fit = (int)(kPartMaxBytes / tile_part);
   if (tiles_fit < 3) tiles_fit = 3;
   const int q_per_cta_max = 4 * (tiles_fit - 2 * prm.nparts > 1 ? tiles_fit - 2 * prm.nparts : 1);
+  const size_t half_sm = kSmemPerSm / 2 - kSmemCtaOverhead;
   for (int q_lo = 0; q_lo < total_q;) {
-    int q_hi = total_q;
-    int grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
-    if ((long)grid * q_per_cta_max < (long)(q_hi - q_lo)) q_hi = q_lo + grid * q_per_cta_max;
+    int cps = cps_want, q_hi = total_q, grid = 0;
+    size_t fixed = 0;
+    for (;;) {
+      // several CTAs per SM only if they are really co-resident (each within 1/cps of the shared memory with a ring
+      // of at least 3 units per warp): otherwise the extra CTAs would run as a second wave
+      const int sms = num_sms() * cps;
+      q_hi = total_q;
+      grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
+      if ((long)grid * q_per_cta_max < (long)(q_hi - q_lo)) q_hi = q_lo + grid * q_per_cta_max;
+      grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
+      const int qmax = cdiv(q_hi - q_lo, grid);
+      prm.max_tiles = cdiv(qmax, 4) + 2 * prm.nparts;
+      fixed = (size_t)prm.max_tiles * tile_part + sums + xbytes + 128;
+      if (cps > 1 && fixed + (size_t)kWarps * 3 * kSlotBytes > kSmemPerSm / cps - kSmemCtaOverhead) { --cps; continue; }
+      break;
+    }
     if (prm.nranks > 0 && (q_lo != 0 || q_hi != total_q)) return QEFT_E_UNSUPPORTED;   // the fused gather signals once per launch
     prm.q_lo = q_lo; prm.q_hi = q_hi;
-    grid = sms < (q_hi - q_lo) ? sms : (q_hi - q_lo);
-    const int qmax = cdiv(q_hi - q_lo, grid);
-    prm.max_tiles = cdiv(qmax, 4) + 2 * prm.nparts;
-    const size_t fixed = (size_t)prm.max_tiles * tile_part + sums + xbytes + 128;
-    // two CTAs per SM (this launch's and, under programmatic dependent launch, the next one's) when the ring
-    // still gets at least 4 units per warp; else the whole SM
-    size_t budget = kSmemPerSm / 2 - kSmemCtaOverhead;
-    if (fixed + (size_t)kWarps * 4 * kSlotBytes > budget) budget = kSmemPerSm - kSmemCtaOverhead;
+    // one CTA per SM: half of the SM when the ring still gets at least 4 units per warp (so that the next launch's CTA
+    // can be co-resident under programmatic dependent launch), else the whole SM; cps CTAs per SM: 1/cps each
+    size_t budget = cps > 1 ? kSmemPerSm / cps - kSmemCtaOverhead : half_sm;
+    if (cps == 1 && fixed + (size_t)kWarps * 4 * kSlotBytes > budget) budget = kSmemPerSm - kSmemCtaOverhead;
     if (fixed + (size_t)kWarps * 2 * kSlotBytes > budget) return QEFT_E_UNSUPPORTED;
     int depth = (int)((budget - fixed) / ((size_t)kWarps * kSlotBytes));
     if (depth_env > 0 && depth > depth_env) depth = depth_env;
