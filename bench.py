@@ -159,8 +159,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"llama2-{model} decode b1, packed QuantLinear stack w4 g128 r128",
-                   "sample": f"1 of {nl} decoder blocks per step (7 dequant+matmul calls); tok/s extrapolated x{nl}"},
+        "config": {"workload": (f"llama2-{model} decode b1: {nl} decoder blocks x 7 packed QuantLinear (w4 g128 r128)"),
+                   "sample": f"1 of {nl} decoder blocks per step (7 dequant+matmul calls on the host CPU); tok/s extrapolated x{nl}",
+                   "algorithmic_bytes_per_step": int(nbytes)},
         "decode_tok_s": 1.0 / (t * nl),
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"one llama2-{model} decoder block (7 linears, {nbytes} algorithmic bytes) per step, "

@@ -764,10 +764,11 @@ gemv_w4_kernel(const GemvParams p) {
     }
   }
   if (p.nranks > 0) {
-    // publish: all of this CTA's peer stores are visible system-wide, then count the CTA; the last one signals
-    __threadfence_system();
+    // publish: the CTA's peer stores happen-before the barrier, thread 0's system-scope fence is cumulative over them;
+    // then count the CTA; the last one signals every rank
     __syncthreads();
     if (tid == 0) {
+      __threadfence_system();
       const unsigned old = atomicAdd(p.local_count, 1u);
       if (old == gridDim.x - 1) {
         *p.local_count = 0u;                         // ready for the next step
