@@ -10,8 +10,12 @@ N > 1 workload (configs[4]): Llama-2-70B shapes, every linear column-sharded ove
 all-gather of each projection group's output over NVLink; strong scaling (total work fixed).
 
 `--impl reference`: the reference has no CPU implementation of this path (every forward calls its CUDA
-extension), so this arm times the oracle's restatement of the reference arithmetic ("torch dequant+matmul on
-CPU", BASELINE.json configs[0]) with all host threads on a bounded sample: one decoder block per step.
+extension).  When `oracle/_ref/qeft_cuda_ref.so` (the reference's own kernels, recompiled for sm_100a by
+oracle/build_ref.py) and a GPU are present, this arm runs the reference's decode path as the reference runs it: per
+decoder block seven `gemv_4bit_qeft` calls plus o_proj's `index_select` (qeft/qlinear.py:244-304), eager launches on
+the legacy default stream, same shapes and byte accounting as our arm.  Otherwise it times the oracle's restatement of
+the reference arithmetic ("torch dequant+matmul on CPU", BASELINE.json configs[0]) with all host threads on a bounded
+sample: one decoder block per step.
 """
 from __future__ import annotations
 
@@ -46,6 +50,8 @@ def parse():
     ap.add_argument("--gather", default="nccl", choices=["fused", "nccl"],
                     help="N > 1: one NCCL all-gather per launch group (default; measured faster at N = 2 this round) or the "
                          "all-gather fused into the GEMV epilogue (peer stores over NVLink + arrival counters)")
+    ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the oracle's CPU port even when "
+                                                             "the reference's own kernels (oracle/_ref) are available")
     ap.add_argument("--no-gemm", action="store_true", help="skip the prefill GEMM / backward extras (M=2048 TFLOP/s)")
     return ap.parse_args()
 
@@ -145,10 +151,114 @@ def cpu_block_baseline(model="7b", reps=1, warm=0, threads=None):
     return nbytes, times, threads
 
 
+def reference_kernels_arm(args, ref):
+    """The reference's own CUDA kernels (oracle/_ref) on this GPU: one decode token = 7 gemv_4bit_qeft per block."""
+    import torch
+
+    from qeft_b200.synth import LLAMA_SHAPES       # shape table only; no kernel of ours runs in this arm
+
+    torch.cuda.set_device(0)
+    model = args.model or ("7b" if args.gpus == 1 else "70b")
+    h, f, nl, kv = LLAMA_SHAPES[model]
+    nl = args.layers or nl
+    r, G, m = 128, 128, 1
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0)
+    names = (("q", h, h), ("k", kv, h), ("v", kv, h), ("o", h, h), ("gate", f, h), ("up", f, h), ("down", h, f))
+    blocks, nbytes = [], 0
+    for _ in range(nl):
+        blk = []
+        for name, N, K in names:
+            zero = torch.randint(0, 16, (K // G, N), device="cuda", generator=gen).float()
+            scale = (torch.rand((K // G, N), device="cuda", generator=gen) * 0.010 + 0.002).half()
+            t = {"qweight": torch.randint(-32768, 32768, (N // 4, K), dtype=torch.int16, device="cuda", generator=gen),
+                 "scales": scale, "scaled_zeros": (-(zero * scale.float())).half(),
+                 "oweight_interleaved": (torch.randn((N // 2, 2 * r), device="cuda", generator=gen) * 0.02).half(),
+                 "N": N, "K": K}
+            if name == "o":      # qlinear.py:275: index_select(x, -1, reorder_ids) ahead of the GEMV
+                t["reorder_ids"] = torch.randperm(K, device="cuda", generator=gen)
+            blk.append(t)
+            nbytes += N * (K - r) // 2 + 4 * N * ((K - r) // G) + 2 * N * r + 2 * K * m + 2 * N * m
+        blocks.append(blk)
+    x_h = torch.randn((m, h), device="cuda", generator=gen).half()
+    x_f = torch.randn((m, f), device="cuda", generator=gen).half()
+
+    def step():
+        y = None
+        for blk in blocks:
+            for t in blk:
+                x = x_f if t["K"] == f else x_h
+                if "reorder_ids" in t:
+                    x = torch.index_select(x, -1, t["reorder_ids"])
+                y = ref.gemv_4bit_qeft(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight_interleaved"],
+                                       m, t["N"], t["K"], G)
+        return y
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(step, args.steps)
+    clocks = sampler.stop()
+    xh, xf = torch.randn(x_h.shape).half().pin_memory(), torch.randn(x_f.shape).half().pin_memory()
+    yh = torch.empty((m, h), dtype=torch.float16).pin_memory()
+
+    def step_from_host():
+        x_h.copy_(xh, non_blocking=True)
+        x_f.copy_(xf, non_blocking=True)
+        yh.copy_(step(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_from_host()
+    ms_e2e = timed(step_from_host, args.steps)
+    gbs, gbs_e2e = nbytes / ms / 1e6, nbytes / ms_e2e / 1e6
+    what = (f"the reference's own kernels (oracle/_ref/qeft_cuda_ref.so: gemv_cuda_qeft.cu recompiled for sm_100a, "
+            f"launch configuration fixed, see oracle/build_ref.py) on this GPU, {7 * nl} eager gemv_4bit_qeft launches per "
+            f"token on the legacy default stream; the reference has no CPU implementation of this path")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"llama2-{model} decode b1: {nl} decoder blocks x 7 packed QuantLinear (w4 g128 r128)"
+                               + (" on ONE GPU (the reference has no column-sharded mode)" if args.gpus > 1 else ""),
+                   "algorithmic_bytes_per_step": int(nbytes), "device": torch.cuda.get_device_name(0),
+                   "l2_policy": "inputs larger than L2"},
+        "decode_tok_s": 1e3 / ms, "clocks": clocks,
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": what},
+        "e2e": {"value": gbs_e2e, "unit": "GB/s", "tok_s": 1e3 / ms_e2e,
+                "h2d_bytes_per_step": int(2 * (xh.numel() + xf.numel())), "d2h_bytes_per_step": int(2 * yh.numel())},
+        "gpu_launches": 0, "reference_gpu_launches": int(7 * nl * args.steps),
+    }
+    if args.layers:
+        line["config"]["INVALID"] = "reduced layer count (debug run)"
+    print(json.dumps(line), flush=True)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not args.cpu_port:
+        try:
+            import torch
+            from oracle import build_ref
+            ref = build_ref.load() if torch.cuda.is_available() else None
+        except Exception as e:  # noqa: BLE001  (a module built against another libtorch: fall back to the CPU port)
+            print(f"bench.py: oracle/_ref not usable ({e}); timing the CPU port", file=sys.stderr)
+            ref = None
+        if ref is not None:
+            return reference_kernels_arm(args, ref)
     model = args.model or "7b"
     from qeft_b200.synth import LLAMA_SHAPES
     nl = LLAMA_SHAPES[model][2]
