@@ -116,3 +116,50 @@ def test_algorithmic_bytes_match_baseline_md():
     assert oracle.gemv_algorithmic_bytes(4096, 11008) == 24_753_664
     per_layer = 4 * 9_699_328 + 2 * 26_053_120 + 24_753_664
     assert per_layer == 115_657_216
+
+
+# ---- forward arithmetic: outputs of the reference's own CUDA kernels, run on a B200 ---------------------------------
+# (tests/golden/make_reference_kernel_vectors.py; the kernels come from oracle/build_ref.py)
+def _kernel_vectors():
+    import os
+    p = os.path.join(os.path.dirname(__file__), "golden", "reference_kernel_vectors.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden/reference_kernel_vectors.npz not generated yet")
+    return np.load(p)
+
+
+def test_oracle_forward_matches_reference_kernel_outputs():
+    g = _kernel_vectors()
+    cases = [str(c) for c in g["cases"]]
+    assert len(cases) >= 9
+    kinds = set()
+    for i, c in enumerate(cases):
+        kind, N, K, r, G, m = c.split(":")
+        N, K, r, G, m = int(N), int(K), int(r), int(G), int(m)
+        kinds.add((kind, G == K))
+        ow = g[f"c{i}_oweight"] if r > 0 else None
+        got = oracle.forward(g[f"c{i}_x"], g[f"c{i}_qweight"], g[f"c{i}_scales"], g[f"c{i}_scaled_zeros"], ow, None,
+                             group_size=G)
+        want = g[f"c{i}_y_ref"]
+        assert got.shape == want.shape == (m, N) and want.dtype == np.float16
+        err = np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))) / np.max(np.abs(want.astype(np.float64)))
+        # the reference rounds each dequantised weight to fp16 and keeps fp16 partial sums; the oracle accumulates wide
+        assert err <= 4e-3, (c, err)
+        if r > 0:
+            # the interleaved outlier layout the GEMV kernel consumed is what the oracle's packer makes of `oweight`
+            assert np.array_equal(oracle.pack_oweight(ow).view(np.uint16), g[f"c{i}_oweight_interleaved"].view(np.uint16))
+    assert {("gemv_qeft", False), ("gemv_qeft", True), ("gemv", False), ("gemm", False)} <= kinds
+
+
+def test_reference_kernel_vectors_detect_a_wrong_layout():
+    """The pin has teeth: swapping two nibble positions or dropping the outlier override moves the oracle far outside
+    the tolerance the real layout meets."""
+    g = _kernel_vectors()
+    i = 1                                  # gemv_qeft 128x512 r=128 m=2
+    x, qw, s, z, ow = (g[f"c{i}_{k}"] for k in ("x", "qweight", "scales", "scaled_zeros", "oweight"))
+    want = g[f"c{i}_y_ref"].astype(np.float64)
+    rel = lambda y: np.max(np.abs(y.astype(np.float64) - want)) / np.max(np.abs(want))  # noqa: E731
+    assert rel(oracle.forward(x, qw, s, z, ow)) <= 4e-3
+    assert rel(oracle.forward(x, qw, s, z, None)) > 5e-2                       # int4 columns instead of outlier columns
+    swapped = ((qw.view(np.uint16) >> 4) & 0x000f | (qw.view(np.uint16) << 4) & 0x00f0 | qw.view(np.uint16) & 0xff00).view(np.int16)
+    assert rel(oracle.forward(x, swapped, s, z, ow)) > 5e-2                    # two nibbles of every word exchanged

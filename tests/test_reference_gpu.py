@@ -64,6 +64,26 @@ def test_gemv_qeft_three_way(N, K, r, m):
 
 
 @needs_ref
+@pytest.mark.parametrize("m", [1, 2, 5])
+@pytest.mark.parametrize("N,K,r", [(256, 512, 128), (512, 2048, 64)])
+def test_gemv_qeft_per_channel_three_way(N, K, r, m):
+    """group_size != 128 sends the reference to gemv_kernel_qeft_perchannel (gemv_cuda_qeft.cu:461-): scales [1, N]."""
+    from qeft_b200 import qeft_cuda
+    L = oracle.synth_layer(N, K, r=r, G=K, seed=7 * N + m)
+    D = {k: dev(L[k]) for k in ("qweight", "scales", "scaled_zeros", "oweight_interleaved")}
+    assert L["scales"].shape == (1, N)
+    x = np.random.default_rng(30 + m).standard_normal((m, K)).astype(np.float16)
+    xd = dev(x)
+    y_ref = ref.gemv_4bit_qeft(xd, D["qweight"], D["scales"], D["scaled_zeros"], D["oweight_interleaved"], m, N, K, K)
+    y_our = qeft_cuda.gemv_4bit_qeft(xd, D["qweight"], D["scales"], D["scaled_zeros"], D["oweight_interleaved"], m, N, K, K)
+    torch.cuda.synchronize()
+    want = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], None, group_size=K)
+    e_ref, e_our = rel(y_ref.cpu().numpy(), want), rel(y_our.cpu().numpy(), want)
+    print(f"gemv_qeft per-channel {N}x{K} m={m}: ref-oracle {e_ref:.2e}  ours-oracle {e_our:.2e}")
+    assert e_ref <= 4e-3 and e_our <= 1e-3 and e_our <= e_ref + 1e-4
+
+
+@needs_ref
 @pytest.mark.parametrize("m", [1, 4, 7])
 @pytest.mark.parametrize("N,K", [(256, 512), (1024, 2048)])
 def test_gemv_plain_three_way(N, K, m):
