@@ -369,6 +369,15 @@ def run_ours(args):
         torch.cuda.empty_cache()
         extra["prefill_finetune"] = bench_gemm(model)
         stack = None
+    if not args.no_gemm and world > 1:
+        # configs[4], prefill half: the same shapes, M = 2048 tokens, every linear column-sharded; all three exchanges
+        stack.graph = None
+        del stack
+        stack = None
+        torch.cuda.empty_cache()
+        pre = bench_prefill_sharded(model, rank, world, local, barrier, layers=args.layers)
+        if rank == 0:
+            extra["prefill_sharded"] = pre
 
     if rank == 0:
         ms_step = ms / args.steps
@@ -424,6 +433,51 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
         os._exit(0)
+
+
+def bench_prefill_sharded(model, rank, world, local, barrier, M=2048, steps=3, layers=None):
+    """70B-shape prefill, M tokens, N-sharded over `world` ranks: TFLOP/s of the whole job (max-over-ranks time) with
+    no exchange (each rank keeps its slab), with the all-gather fused into the GEMM epilogue, and with NCCL."""
+    import torch
+    import torch.distributed as dist
+
+    from qeft_b200.prefill import PackedPrefillStack
+
+    _, tpeak, src = measured_peaks()
+    st = PackedPrefillStack(model, M=M, layers=layers, shard=(rank, world), device=f"cuda:{local}", fast_synth=True)
+    flops_all = st.flops_per_step() * world
+    out = {"M": M, "layers": st.nlayers, "launches_per_step": st.launches_per_step(), "flops_per_step": flops_all,
+           "tensor_peak_TFLOPs_per_gpu": tpeak, "peak_source": src,
+           "sent_bytes_per_rank_per_step": st.gathered_bytes_per_step(), "modes": {}}
+
+    def timed():
+        st.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            st.step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for mode in ("local", "fused", "nccl"):
+        if mode == "fused":
+            st.enable_fused_gather(dist.group.WORLD)
+        elif mode == "nccl":
+            st.enable_allgather(dist.group.WORLD)
+        ms = timed()
+        tf = flops_all / ms / 1e9
+        out["modes"][mode] = {"ms_per_step": ms, "TFLOPs": tf, "TFLOPs_per_gpu": tf / world,
+                              "frac_of_tensor_peak": tf / world / tpeak}
+    out["note"] = ("local = no exchange (each rank keeps its [M, N/P] slab); fused = every output tile stored into every "
+                   "rank's [M, N] buffer by the GEMM epilogue (peer stores over NVLink, arrival counters); nccl = "
+                   "all_gather_into_tensor + one permuting copy per launch")
+    del st
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_gemm(model, M=2048, iters=10):

@@ -141,6 +141,18 @@ QEFT_API int qeft_gemm_w4(const void* x, const void* qweight, const void* scales
                  int dtype, unsigned flags, qeft_stream_t stream);
 
 /*
+ * Column-sharded prefill: the same GEMM on this rank's N output features (a row slab of the packed
+ * layer), with the all-gather fused into the epilogue: every output tile is stored into the gathered [M, y_ld] buffer
+ * of EVERY rank at this rank's column offset (gather->y_peer[p][0], peer-mapped pointers over NVLink), tile by tile
+ * while other tiles are still computing.  Signalling as in qeft_gemv_w4_multi_gather: the launch's last CTA adds 1
+ * (release, system scope) to gather->done_peer[p] of every rank; a launch whose x is a gathered buffer passes that
+ * launch's local counter as gather->wait_flag (its TMA producer acquires it before the first load).
+ */
+QEFT_API int qeft_gemm_w4_gather(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
+                        const void* oweight, const void* bias, int M, int N, int K, int r, int G, int dtype,
+                        unsigned flags, const qeft_gather_t* gather, qeft_stream_t stream);
+
+/*
  * Backward wrt the input:  dx[M, K] = dy[M, N] . Wdense   (same packed bytes, contraction over N).
  * The math BASELINE.json defines for QuantMatMulQEFT.backward (the reference's qlinear.py:28-44 is
  * not usable).

@@ -42,6 +42,7 @@ SIGNATURES = {
     "qeft_gemv_w4_multi": (_i, [_vp, C.POINTER(GemvPart), _i, _i, _vp, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemv_w4_multi_gather": (_i, [_vp, C.POINTER(GemvPart), _i, _i, _vp, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),
     "qeft_gemm_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
+    "qeft_gemm_w4_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),
     "qeft_gemm_w4_dx": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_dow": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_pack_w4": (_i, [_vp, _vp, _i, _i, _vp]),

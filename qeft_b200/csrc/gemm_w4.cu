@@ -69,6 +69,16 @@ struct GemmParams {
   int nkb;                 // + outlier k-blocks r / 64
   int dbg;                 // QEFT_GEMM_DEBUG bits (bisecting only; results are wrong when set): 1 = no dequant
                            // math, 2 = no activation loads
+  // output row pitch and, for the column-sharded prefill (all-gather fused into the epilogue, qeft_gemm_w4_gather):
+  // every rank's gathered buffer (offset to THIS rank's columns), the arrival counters, the flag of the launch whose
+  // gathered output is this launch's x
+  int y_ld;
+  int nranks;              // 0: plain launch, y only
+  __half* y_peer[QEFT_MAX_RANKS];
+  uint32_t* done_peer[QEFT_MAX_RANKS];
+  uint32_t* local_count;
+  const uint32_t* wait_flag;
+  const uint32_t* epoch;
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row groups 1024
@@ -135,6 +145,17 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
       pdl_wait();                                   // x is the previous kernel's output
+      if (p.wait_flag) {
+        // column-sharded chain: x is the gathered output of an earlier launch; every rank's slice has landed once that
+        // launch's arrival counter reaches epoch x ranks.  The slices were written by generic-proxy stores (of this and
+        // other GPUs) and are read by TMA: order the two proxies after the acquire.
+        const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.epoch) * (uint32_t)p.nranks;
+        uint32_t got;
+        do {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.wait_flag) : "memory");
+        } while ((int)(got - want) < 0);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
       for (int st = 0; st < nst; ++st) {
         const int s = st % kXStages, use = st / kXStages;
         if (use > 0) mbar_wait(x_empty(s), (uint32_t)((use - 1) & 1));
@@ -315,7 +336,14 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
           const int row = pass * 8 + (lane >> 2), piece = lane & 3;
           const int tok = tok0 + 32 * tc + row;
           const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + piece * 8);
-          if (tok < p.M) *reinterpret_cast<uint4*>(p.y + (size_t)tok * p.N + fw + piece * 8) = val;
+          if (tok < p.M) {
+            const size_t off = (size_t)tok * (size_t)p.y_ld + (size_t)(fw + piece * 8);
+            if (p.nranks == 0) {
+              *reinterpret_cast<uint4*>(p.y + off) = val;
+            } else {
+              for (int pr = 0; pr < p.nranks; ++pr) *reinterpret_cast<uint4*>(p.y_peer[pr] + off) = val;   // NVLink stores
+            }
+          }
         }
         __syncwarp();
       }
@@ -328,6 +356,18 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+  if (p.nranks > 0 && tid == 0) {
+    // publish (same protocol as the decode GEMV): the CTA's peer stores happen-before the barrier above, this
+    // thread's system-scope fence is cumulative over them; the last CTA of the launch signals every rank
+    __threadfence_system();
+    const unsigned old = atomicAdd(p.local_count, 1u);
+    if (old == gridDim.x * gridDim.y - 1) {
+      *p.local_count = 0u;
+      __threadfence_system();
+      for (int pr = 0; pr < p.nranks; ++pr)
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.done_peer[pr]) : "memory");
+    }
   }
 }
 
@@ -415,17 +455,18 @@ static int launch_gemm(const void* x, const GemmParams& prm, unsigned flags, cud
 
 using namespace qeft;
 
-extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
-                            const void* oweight, const void* bias, void* y, int M, int N, int K, int r, int G,
-                            int dtype, unsigned flags, qeft_stream_t stream) {
-  if (!x || !qweight || !scales || !scaled_zeros || !y) return QEFT_E_NULL;
+static int gemm_entry(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
+                      const void* oweight, const void* bias, void* y, int M, int N, int K, int r, int G,
+                      int dtype, unsigned flags, const qeft_gather_t* gat, qeft_stream_t stream) {
+  if (!x || !qweight || !scales || !scaled_zeros || (!y && !gat)) return QEFT_E_NULL;
   if (dtype != QEFT_DT_F16 && dtype != QEFT_DT_BF16) return QEFT_E_DTYPE;
   if (G == -1) G = K;
   if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 64 != 0 || G <= 0 || G % 64 != 0 || K % G != 0) return QEFT_E_SHAPE;
   if (r < 0 || r % 64 != 0 || r >= K) return QEFT_E_SHAPE;
   if (r > 0 && !oweight) return QEFT_E_NULL;
-  if (!check_align16(x) || !check_align16(qweight) || !check_align16(y) || (r > 0 && !check_align16(oweight))) return QEFT_E_ALIGN;
-  GemmParams prm;
+  if (!check_align16(x) || !check_align16(qweight) || (y && !check_align16(y)) || (r > 0 && !check_align16(oweight)))
+    return QEFT_E_ALIGN;
+  GemmParams prm = {};
   prm.qw = static_cast<const uint8_t*>(qweight);
   prm.scales = static_cast<const __half*>(scales);
   prm.szeros = static_cast<const __half*>(scaled_zeros);
@@ -435,6 +476,22 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
   prm.M = M; prm.N = N; prm.K = K; prm.r = r; prm.G = G;
   prm.nkb_q = (K - r) / kBK;
   prm.nkb = prm.nkb_q + r / kBK;
+  prm.y_ld = N;
+  if (gat) {
+    if (gat->nranks < 1 || gat->nranks > QEFT_MAX_RANKS || !gat->local_count || !gat->epoch) return QEFT_E_SHAPE;
+    if (gat->y_ld < N || gat->y_ld % 8 != 0) return QEFT_E_SHAPE;
+    prm.nranks = gat->nranks;
+    prm.y_ld = gat->y_ld;
+    for (int pr = 0; pr < gat->nranks; ++pr) {
+      if (!gat->y_peer[pr][0] || !gat->done_peer[pr]) return QEFT_E_NULL;
+      if (!check_align16(gat->y_peer[pr][0])) return QEFT_E_ALIGN;
+      prm.y_peer[pr] = static_cast<__half*>(gat->y_peer[pr][0]);
+      prm.done_peer[pr] = gat->done_peer[pr];
+    }
+    prm.local_count = gat->local_count;
+    prm.wait_flag = gat->wait_flag;
+    prm.epoch = gat->epoch;
+  }
   static const int dbg_env = getenv("QEFT_GEMM_DEBUG") ? atoi(getenv("QEFT_GEMM_DEBUG")) : 0;
   prm.dbg = dbg_env;
   static const int cfg_env = getenv("QEFT_GEMM_CFG") ? atoi(getenv("QEFT_GEMM_CFG")) : 0;
@@ -444,7 +501,19 @@ extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scal
   // bf16: x, oweight and y are bf16 (bias, scales, scaled zeros stay fp16 as in the checkpoint); the int4 columns are
   // dequantised in fp32 with one rounding to bf16
   if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs);
-  if (cfg_env == 3 && N % 256 == 0) return launch_gemm<1, 256, true, false>(x, prm, flags, cs);
+  if (cfg_env == 3 && N % 256 == 0 && !gat) return launch_gemm<1, 256, true, false>(x, prm, flags, cs);
   return launch_gemm<1, 256, false, false>(x, prm, flags, cs);
 }
 
+extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
+                            const void* oweight, const void* bias, void* y, int M, int N, int K, int r, int G,
+                            int dtype, unsigned flags, qeft_stream_t stream) {
+  return gemm_entry(x, qweight, scales, scaled_zeros, oweight, bias, y, M, N, K, r, G, dtype, flags, nullptr, stream);
+}
+
+extern "C" int qeft_gemm_w4_gather(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
+                                   const void* oweight, const void* bias, int M, int N, int K, int r, int G, int dtype,
+                                   unsigned flags, const qeft_gather_t* gather, qeft_stream_t stream) {
+  if (!gather) return QEFT_E_NULL;
+  return gemm_entry(x, qweight, scales, scaled_zeros, oweight, bias, nullptr, M, N, K, r, G, dtype, flags, gather, stream);
+}

@@ -154,6 +154,24 @@ def gemm_w4(x, qweight, scales, scaled_zeros, oweight, bias, *, group_size=128, 
     return out
 
 
+
+def gemm_w4_gather(x, qweight, scales, scaled_zeros, oweight, bias, gather, *, group_size=128, pdl=None):
+    """Column-sharded prefill: :func:`gemm_w4` on this rank's row slab, every output tile stored by the kernel into
+    every rank's gathered ``[M, y_ld]`` buffer (``gather``: a prepared ``_lib.Gather``; include/qeft_b200.h)."""
+    _need_cuda(x, qweight, scales, scaled_zeros, oweight, bias)
+    dt = _dt(x)
+    if not x.is_contiguous():
+        raise RuntimeError("gemm_w4_gather: x must be contiguous (it is a gathered buffer)")
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = qweight.shape[0] * 4
+    r = 0 if oweight is None else oweight.shape[1]
+    with torch.cuda.device(x.device):
+        st = _lib.load().qeft_gemm_w4_gather(_ptr(x), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
+                                             _ptr(bias), M, N, K, r, group_size, dt, _flags(pdl), C.byref(gather),
+                                             _stream(x))
+    _lib.check(st, "qeft_gemm_w4_gather")
+
 def gemm_w4_dx(dy, qweight, scales, scaled_zeros, oweight, K, *, group_size=128, out=None, pdl=None):
     """``dx[M, K] = dy[M, N] . Wdense``."""
     _need_cuda(dy, qweight, scales, scaled_zeros, oweight)

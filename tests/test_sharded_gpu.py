@@ -69,3 +69,66 @@ def test_fused_gather_equals_nccl_allgather():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---- prefill: the all-gather fused into the tcgen05 GEMM's epilogue --------------------------------------------------
+def _prefill_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from qeft_b200 import qeft_cuda
+        from qeft_b200.prefill import NAMES, PackedPrefillStack
+        from qeft_b200.synth import synth_tensors
+        shape = (512, 1024, 2, 256)                  # hidden, ffn, blocks, kv width: every N splits into 2 x k x 128 rows
+        M = 300                                      # ragged: the last 256-token tile is partial
+        kw = dict(M=M, seed=5, shard=(rank, world), device=f"cuda:{rank}", fast_synth=False, shard_from_full=True)
+        nccl = PackedPrefillStack(shape, **kw)
+        nccl.enable_allgather(dist.group.WORLD)
+        nccl.step()
+        torch.cuda.synchronize()
+        fused = PackedPrefillStack(shape, **kw)
+        fused.enable_fused_gather(dist.group.WORLD)
+        ok = True
+        for it in range(3):
+            for s in range(2):
+                for n in NAMES:
+                    fused.y_full[s][n].zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            fused.step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            for li in range(2):
+                for pi, n in enumerate(NAMES):
+                    got = fused.y_full[li % 2][n]
+                    ok = ok and torch.equal(got, nccl.y_full[li % 2][n])
+                    # and against the unsharded layer on this rank
+                    t = synth_tensors(fused.full[n], fused.kin[n], 128, 128, seed=5 * 100003 + li * 16 + pi,
+                                      device=f"cuda:{rank}")
+                    x = fused.x_f if n == "down" else fused.x_h
+                    want = qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None)
+                    ok = ok and torch.equal(got, want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_prefill_fused_gather_equals_nccl_and_unsharded():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_prefill_worker, args=(rank, world, port, q)) for rank in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
