@@ -463,9 +463,14 @@ def bench_prefill_sharded(model, rank, world, local, barrier, M=2048, steps=3, l
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    for mode in ("local", "fused", "nccl"):
+    for mode in ("local", "fused", "fused_multicast", "nccl"):
         if mode == "fused":
-            st.enable_fused_gather(dist.group.WORLD)
+            st.enable_fused_gather(dist.group.WORLD, multicast=False)
+        elif mode == "fused_multicast":
+            st.enable_fused_gather(dist.group.WORLD, multicast=True)
+            if not st.multicast:
+                out["modes"][mode] = {"unavailable": "the symmetric allocation has no multicast mapping on this box"}
+                continue
         elif mode == "nccl":
             st.enable_allgather(dist.group.WORLD)
         ms = timed()
@@ -473,7 +478,8 @@ def bench_prefill_sharded(model, rank, world, local, barrier, M=2048, steps=3, l
         out["modes"][mode] = {"ms_per_step": ms, "TFLOPs": tf, "TFLOPs_per_gpu": tf / world,
                               "frac_of_tensor_peak": tf / world / tpeak}
     out["note"] = ("local = no exchange (each rank keeps its [M, N/P] slab); fused = every output tile stored into every "
-                   "rank's [M, N] buffer by the GEMM epilogue (peer stores over NVLink, arrival counters); nccl = "
+                   "rank's [M, N] buffer by the GEMM epilogue (peer stores over NVLink, arrival counters); fused_multicast = the "
+                   "same with ONE store per tile piece to the NVLS multicast mapping (the NVSwitch replicates it); nccl = "
                    "all_gather_into_tensor + one permuting copy per launch")
     del st
     torch.cuda.empty_cache()

@@ -120,6 +120,10 @@ typedef struct {
   uint32_t* local_count;
   const uint32_t* wait_flag;                           /* local arrival counter of the launch depended on, or NULL */
   const uint32_t* epoch;
+  /* qeft_gemm_w4_gather only, optional: the MULTICAST mapping (NVLS; torch symmetric memory's multicast_ptr) of the
+   * gathered buffer of part i, offset to this rank's columns.  When set, every tile is stored once to this address
+   * and the NVSwitch replicates it to all ranks (egress bytes / (nranks - 1)); y_peer is then unused. */
+  void* y_mc[QEFT_GEMV_MAX_PARTS];
 } qeft_gather_t;
 
 QEFT_API int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,

@@ -28,7 +28,8 @@ class Gather(C.Structure):
     _fields_ = [("nranks", C.c_int), ("y_ld", C.c_int),
                 ("y_peer", (C.c_void_p * GEMV_MAX_PARTS) * MAX_RANKS),
                 ("done_peer", C.c_void_p * MAX_RANKS),
-                ("local_count", C.c_void_p), ("wait_flag", C.c_void_p), ("epoch", C.c_void_p)]
+                ("local_count", C.c_void_p), ("wait_flag", C.c_void_p), ("epoch", C.c_void_p),
+                ("y_mc", C.c_void_p * GEMV_MAX_PARTS)]
 
 
 _vp, _i, _u = C.c_void_p, C.c_int, C.c_uint

@@ -75,6 +75,7 @@ struct GemmParams {
   int y_ld;
   int nranks;              // 0: plain launch, y only
   __half* y_peer[QEFT_MAX_RANKS];
+  __half* y_mc;            // multicast mapping of the gathered buffer (one store reaches every rank), or null
   uint32_t* done_peer[QEFT_MAX_RANKS];
   uint32_t* local_count;
   const uint32_t* wait_flag;
@@ -340,6 +341,11 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
             const size_t off = (size_t)tok * (size_t)p.y_ld + (size_t)(fw + piece * 8);
             if (p.nranks == 0) {
               *reinterpret_cast<uint4*>(p.y + off) = val;
+            } else if (p.y_mc) {
+              // one store to the multicast address: the switch replicates it to every rank (multimem.st lowers to
+              // this same STG.128 on the multicast mapping)
+              asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y_mc + off), "r"(val.x),
+                           "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
             } else {
               for (int pr = 0; pr < p.nranks; ++pr) *reinterpret_cast<uint4*>(p.y_peer[pr] + off) = val;   // NVLink stores
             }
@@ -482,8 +488,10 @@ static int gemm_entry(const void* x, const void* qweight, const void* scales, co
     if (gat->y_ld < N || gat->y_ld % 8 != 0) return QEFT_E_SHAPE;
     prm.nranks = gat->nranks;
     prm.y_ld = gat->y_ld;
+    prm.y_mc = static_cast<__half*>(gat->y_mc[0]);
+    if (prm.y_mc && !check_align16(prm.y_mc)) return QEFT_E_ALIGN;
     for (int pr = 0; pr < gat->nranks; ++pr) {
-      if (!gat->y_peer[pr][0] || !gat->done_peer[pr]) return QEFT_E_NULL;
+      if ((!prm.y_mc && !gat->y_peer[pr][0]) || !gat->done_peer[pr]) return QEFT_E_NULL;
       if (!check_align16(gat->y_peer[pr][0])) return QEFT_E_ALIGN;
       prm.y_peer[pr] = static_cast<__half*>(gat->y_peer[pr][0]);
       prm.done_peer[pr] = gat->done_peer[pr];

@@ -88,7 +88,9 @@ class PackedPrefillStack:
         self.y_full = [{n: torch.empty((M, self.full[n]), dtype=torch.float16, device=self.device) for n in NAMES}
                        for _ in range(2)]
 
-    def enable_fused_gather(self, process_group):
+    def enable_fused_gather(self, process_group, multicast=True):
+        """``multicast``: store each tile once to the NVLS multicast mapping of the gathered buffer (the NVSwitch
+        replicates it to all ranks) when the symmetric allocation has one; else one store per rank."""
         import torch.distributed._symmetric_memory as symm_mem
         P, M = self.world, self.M
         nlaunch = 7 * self.nlayers
@@ -99,6 +101,8 @@ class PackedPrefillStack:
         buf.zero_()
         hdl = symm_mem.rendezvous(buf, process_group)
         self._symm = (buf, hdl)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if multicast else 0
+        self.multicast = bool(mc)
         self.epoch = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self.local_counts = torch.zeros((nlaunch,), dtype=torch.int32, device=self.device)
         offs, off = [], flag_bytes
@@ -121,6 +125,8 @@ class PackedPrefillStack:
                 for pr in range(P):
                     g.y_peer[pr][0] = hdl.buffer_ptrs[pr] + offs[li % 2][n] + 2 * self.rank * (w // P)
                     g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * li_flat
+                if mc:
+                    g.y_mc[0] = mc + offs[li % 2][n] + 2 * self.rank * (w // P)
                 g.local_count = self.local_counts.data_ptr() + 4 * li_flat
                 g.wait_flag = prev_flag
                 g.epoch = self.epoch.data_ptr()
@@ -129,19 +135,20 @@ class PackedPrefillStack:
                 li_flat += 1
             self.gathers.append(row)
         hdl.barrier()
-        self.pg, self.mode = None, "fused"
+        self.pg, self.mode = None, "fused_mc" if mc else "fused"
 
     # ---- one pass -------------------------------------------------------------------------------
     def step(self):
         G = self.G
-        if self.mode == "fused":
+        fused = self.mode in ("fused", "fused_mc")
+        if fused:
             self.epoch.add_(1)
         for li, blk in enumerate(self.blocks):
             s = li % 2
             for n in NAMES:
                 t = blk[n]
                 x = self.x_f if n == "down" else self.x_h
-                if self.mode == "fused":
+                if fused:
                     qeft_cuda.gemm_w4_gather(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], t.get("bias"),
                                              self.gathers[li][n], group_size=G, pdl=self.pdl)
                     continue

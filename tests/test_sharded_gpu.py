@@ -90,9 +90,12 @@ def _prefill_worker(rank, world, port, q):
         nccl.step()
         torch.cuda.synchronize()
         fused = PackedPrefillStack(shape, **kw)
-        fused.enable_fused_gather(dist.group.WORLD)
         ok = True
-        for it in range(3):
+        for it in range(4):
+            if it == 0:
+                fused.enable_fused_gather(dist.group.WORLD, multicast=False)      # one store per rank
+            elif it == 2:
+                fused.enable_fused_gather(dist.group.WORLD, multicast=True)       # NVLS multicast stores, if available
             for s in range(2):
                 for n in NAMES:
                     fused.y_full[s][n].zero_()
