@@ -105,12 +105,16 @@ QEFT_API int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, in
  * Column-sharded decode (no reference counterpart: the reference has no multi-GPU code): the same
  * multi-projection GEMV, but every rank computes its slice of the output features and the kernel's epilogue stores
  * that slice DIRECTLY into the gathered buffer of every rank (peer-mapped pointers over NVLink) -- an all-gather
- * fused into the GEMV, no collective call.  Completion is signalled per launch: the last CTA of the launch adds 1
- * (release, system scope) to every rank's arrival counter `done_peer[p]`; a dependent launch passes that counter
- * as `wait_flag` and spins (acquire, system scope) until it reaches `*epoch * nranks` before it reads its input.
+ * fused into the GEMV, no collective call.  Completion is signalled per launch: every CTA, after ONE system-scope
+ * fence that orders its peer stores, adds its share of QEFT_ARRIVALS_PER_LAUNCH (relaxed, system scope) to every
+ * rank's arrival counter `done_peer[p]`; the shares of a launch add up to exactly QEFT_ARRIVALS_PER_LAUNCH whatever
+ * its grid.  A dependent launch passes that counter as `wait_flag` and spins (acquire, system scope) until it reaches
+ * `*epoch * nranks * QEFT_ARRIVALS_PER_LAUNCH` before it reads its input; with QEFT_F_PDL that counter is the ONLY
+ * ordering between the two launches (no grid-completion wait), so the chain never pays a kernel boundary.
  * `epoch` is a device-resident step counter the caller increments once per decode step (graph-replay friendly).
- * `local_count` is a zero-initialised device word private to this launch (CTA arrival count).
+ * `local_count` is unused (kept for layout compatibility).  x_gather, when given, must be 16-byte aligned.
  */
+#define QEFT_ARRIVALS_PER_LAUNCH 65536u
 #define QEFT_MAX_RANKS 8
 typedef struct {
   int nranks;
@@ -148,8 +152,8 @@ QEFT_API int qeft_gemm_w4(const void* x, const void* qweight, const void* scales
  * Column-sharded prefill: the same GEMM on this rank's N output features (a row slab of the packed
  * layer), with the all-gather fused into the epilogue: every output tile is stored into the gathered [M, y_ld] buffer
  * of EVERY rank at this rank's column offset (gather->y_peer[p][0], peer-mapped pointers over NVLink), tile by tile
- * while other tiles are still computing.  Signalling as in qeft_gemv_w4_multi_gather: the launch's last CTA adds 1
- * (release, system scope) to gather->done_peer[p] of every rank; a launch whose x is a gathered buffer passes that
+ * while other tiles are still computing.  Signalling as in qeft_gemv_w4_multi_gather: every CTA adds its share
+ * of QEFT_ARRIVALS_PER_LAUNCH to gather->done_peer[p] of every rank; a launch whose x is a gathered buffer passes that
  * launch's local counter as gather->wait_flag (its TMA producer acquires it before the first load).
  */
 QEFT_API int qeft_gemm_w4_gather(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,

@@ -47,6 +47,14 @@ __device__ __forceinline__ unsigned short ldg_nc_u16(const void* p) {
 
 // ---- programmatic dependent launch -------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Column-sharded chains: a launch advances every rank's arrival counter by kArrivalsPerLaunch in total, CTA i of a
+// grid of n contributing floor(A (i + 1) / n) - floor(A i / n) (the shares telescope to exactly A for any grid size,
+// so a waiting launch needs to know neither the producer's grid nor its kernel: it waits for epoch x ranks x A).
+constexpr unsigned kArrivalsPerLaunch = 1u << 16;
+__device__ __forceinline__ unsigned arrival_share(unsigned i, unsigned n) {
+  return (unsigned)(((unsigned long long)kArrivalsPerLaunch * (i + 1)) / n) - (unsigned)(((unsigned long long)kArrivalsPerLaunch * i) / n);
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- int4 -> fp16 ------------------------------------------------------------------------

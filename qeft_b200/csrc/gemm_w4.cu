@@ -150,7 +150,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         // column-sharded chain: x is the gathered output of an earlier launch; every rank's slice has landed once that
         // launch's arrival counter reaches epoch x ranks.  The slices were written by generic-proxy stores (of this and
         // other GPUs) and are read by TMA: order the two proxies after the acquire.
-        const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.epoch) * (uint32_t)p.nranks;
+        const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.epoch) * (uint32_t)p.nranks * kArrivalsPerLaunch;
         uint32_t got;
         do {
           asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.wait_flag) : "memory");
@@ -364,16 +364,13 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
   }
   if (p.nranks > 0 && tid == 0) {
-    // publish (same protocol as the decode GEMV): the CTA's peer stores happen-before the barrier above, this
-    // thread's system-scope fence is cumulative over them; the last CTA of the launch signals every rank
+    // publish (same protocol as the decode GEMV): the CTA's stores happen-before the barrier above, this thread's
+    // system-scope fence is cumulative over them and orders them before its relaxed signals; every CTA signals its
+    // share of kArrivalsPerLaunch to every rank
     __threadfence_system();
-    const unsigned old = atomicAdd(p.local_count, 1u);
-    if (old == gridDim.x * gridDim.y - 1) {
-      *p.local_count = 0u;
-      __threadfence_system();
-      for (int pr = 0; pr < p.nranks; ++pr)
-        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.done_peer[pr]) : "memory");
-    }
+    const unsigned inc = arrival_share(blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
+    for (int pr = 0; pr < p.nranks; ++pr)
+      asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p.done_peer[pr]), "r"(inc) : "memory");
   }
 }
 
@@ -484,7 +481,7 @@ static int gemm_entry(const void* x, const void* qweight, const void* scales, co
   prm.nkb = prm.nkb_q + r / kBK;
   prm.y_ld = N;
   if (gat) {
-    if (gat->nranks < 1 || gat->nranks > QEFT_MAX_RANKS || !gat->local_count || !gat->epoch) return QEFT_E_SHAPE;
+    if (gat->nranks < 1 || gat->nranks > QEFT_MAX_RANKS || !gat->epoch) return QEFT_E_SHAPE;
     if (gat->y_ld < N || gat->y_ld % 8 != 0) return QEFT_E_SHAPE;
     prm.nranks = gat->nranks;
     prm.y_ld = gat->y_ld;

@@ -74,6 +74,7 @@ struct GemvParams {
   uint32_t* done_peer[QEFT_MAX_RANKS];
   uint32_t* local_count;
   const uint32_t* wait_flag;
+  int flag_only;          // 1: the arrival counter alone orders this launch after its input (no grid-completion wait)
   const uint32_t* epoch;
 };
 
@@ -323,12 +324,17 @@ gemv_w4_kernel(const GemvParams p) {
   for (int i = tid; i < ntiles * kWarps * 16 * pc; i += kThreads) part[i] = 0.f;
 
   stamp(p, 1);
-  pdl_wait();   // x (and y as a reused buffer) belong to the previous kernel until here
+  // x (and y as a reused buffer) belong to the previous kernel until here.  In the column-sharded chain the input is
+  // the gathered buffer of an earlier launch, complete exactly when that launch's arrival counter says so (every rank,
+  // this one included, stores its slice and then signals with release semantics): the counter alone orders the two
+  // launches, and waiting for the previous GRID to drain as well (its system-scope fences and NVLink stores included)
+  // only adds the kernel-boundary latency to every launch of the chain.
+  if (!p.flag_only) pdl_wait();
   if (p.wait_flag) {
     // column-sharded chain: the launch this one depends on has finished on THIS rank (stream order); wait until every
     // rank's slice of its output has landed here: its arrival counter reaches epoch x ranks
     if (tid == 0) {
-      const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.epoch) * (uint32_t)p.nranks;
+      const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.epoch) * (uint32_t)p.nranks * kArrivalsPerLaunch;
       uint32_t got;
       do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.wait_flag) : "memory");
@@ -352,8 +358,10 @@ gemv_w4_kernel(const GemvParams p) {
     const int live_k = nchunks * 32;
     float4* sums4 = sums;
     const int nitems = m * nsteps * 8;
-    // all global loads of up to kPre passes are issued before the first use (one L2 round trip, not one per pass)
-    constexpr int kPre = 4;
+    // all global loads of up to kPre passes are issued before the first use (one L2 round trip, not one per pass);
+    // with an o_proj gather (qlinear.py:275) up to kPreG passes: the 16 indices of an item as four vector loads,
+    // then the 16 scattered halves -- two dependent round trips for the whole staging instead of two per pass
+    constexpr int kPre = 4, kPreG = 2;
     uint4 pre[kPre][2];
     if (!p.gather) {
 #pragma unroll
@@ -368,6 +376,53 @@ gemv_w4_kernel(const GemvParams p) {
             pre[q][1] = ldg_nc_v4(xg + (size_t)b * K + k0 + 16);
           }
         }
+      }
+    } else {
+      int4 gi[kPreG][4];
+      bool glive[kPreG];
+      const unsigned short* grow[kPreG];
+#pragma unroll
+      for (int q = 0; q < kPreG; ++q) {
+        const int it = q * kThreads + tid;
+        const int sb = it < nitems ? (it >> 3) : 0, b = sb / nsteps, s = sb - b * nsteps;
+        const int k0 = s * 128 + ((it >> 1) & 3) * 32 + 8 * (it & 1);
+        glive[q] = it < nitems && k0 < live_k;
+        grow[q] = reinterpret_cast<const unsigned short*>(xg + (size_t)b * K);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gi[q][j] = make_int4(0, 0, 0, 0);
+        if (glive[q]) {
+          const int4* ip = reinterpret_cast<const int4*>(p.gather + k0);
+          gi[q][0] = __ldg(ip); gi[q][1] = __ldg(ip + 1); gi[q][2] = __ldg(ip + 4); gi[q][3] = __ldg(ip + 5);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kPreG; ++q) {
+        pre[q][0] = pre[q][1] = make_uint4(0u, 0u, 0u, 0u);
+        if (glive[q]) {
+          const unsigned short* xr = grow[q];
+          auto pk = [&](int a, int b2) { return (uint32_t)xr[a] | ((uint32_t)xr[b2] << 16); };
+          pre[q][0] = make_uint4(pk(gi[q][0].x, gi[q][0].y), pk(gi[q][0].z, gi[q][0].w), pk(gi[q][1].x, gi[q][1].y), pk(gi[q][1].z, gi[q][1].w));
+          pre[q][1] = make_uint4(pk(gi[q][2].x, gi[q][2].y), pk(gi[q][2].z, gi[q][2].w), pk(gi[q][3].x, gi[q][3].y), pk(gi[q][3].z, gi[q][3].w));
+        }
+      }
+    }
+    const int npre = p.gather ? kPreG : kPre;
+    // the outlier activations (fp16, legacy MMA): loaded here, stored after the digit passes, so that their round
+    // trip overlaps the conversion work instead of following it
+    const int nxo = m * (r >> 3);
+    const bool xo_early = nxo <= kThreads;
+    uint4 xo_v = make_uint4(0u, 0u, 0u, 0u);
+    if (xo_early && tid < nxo) {
+      const int b = tid / (r >> 3), jj = tid - b * (r >> 3);
+      const __half* xrow = xg + (size_t)b * K;
+      if (p.gather) {
+        const int4* ip = reinterpret_cast<const int4*>(p.gather + K - r + 8 * jj);
+        const int4 a = __ldg(ip), c = __ldg(ip + 1);
+        const unsigned short* xr = reinterpret_cast<const unsigned short*>(xrow);
+        auto pk = [&](int i0, int i1) { return (uint32_t)xr[i0] | ((uint32_t)xr[i1] << 16); };
+        xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
+      } else {
+        xo_v = ldg_nc_v4(xrow + K - r + 8 * jj);
       }
     }
 #pragma unroll 1
@@ -384,23 +439,21 @@ gemv_w4_kernel(const GemvParams p) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) w[j] = 0u;
       if (live) {
-        if (p.gather) {
+        if (pass < npre) {
+          // select the preloaded pair without dynamic register indexing
+          uint4 v0 = pre[0][0], v1 = pre[0][1];
+#pragma unroll
+          for (int q = 1; q < kPre; ++q)
+            if (pass == q) { v0 = pre[q][0]; v1 = pre[q][1]; }
+          w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+        } else if (p.gather) {
           __half tmp[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { tmp[j] = xrow[p.gather[k0 + j]]; tmp[8 + j] = xrow[p.gather[k0 + 16 + j]]; }
 #pragma unroll
           for (int j = 0; j < 8; ++j) w[j] = reinterpret_cast<uint32_t*>(tmp)[j];
         } else {
-          uint4 v0, v1;
-          if (pass < kPre) {
-            // select the preloaded pair without dynamic register indexing
-            v0 = pre[0][0]; v1 = pre[0][1];
-#pragma unroll
-            for (int q = 1; q < kPre; ++q)
-              if (pass == q) { v0 = pre[q][0]; v1 = pre[q][1]; }
-          } else {
-            v0 = ldg_nc_v4(xrow + k0); v1 = ldg_nc_v4(xrow + k0 + 16);
-          }
+          const uint4 v0 = ldg_nc_v4(xrow + k0), v1 = ldg_nc_v4(xrow + k0 + 16);
           w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
         }
       }
@@ -460,7 +513,12 @@ gemv_w4_kernel(const GemvParams p) {
         }
       }
     }
-    if (r > 0) {                                                   // the outlier activations (fp16, legacy MMA)
+    if (xo_early) {
+      if (tid < nxo) {
+        const int b = tid / (r >> 3), jj = tid - b * (r >> 3);
+        *reinterpret_cast<uint4*>(xo + (size_t)b * r + 8 * jj) = xo_v;
+      }
+    } else if (r > 0) {                                            // the outlier activations (fp16, legacy MMA)
       for (int j = tid; j < m * (r >> 3); j += kThreads) {
         const int b = j / (r >> 3), jj = j - b * (r >> 3);
         const __half* xrow = xg + (size_t)b * K;
@@ -764,18 +822,16 @@ gemv_w4_kernel(const GemvParams p) {
     }
   }
   if (p.nranks > 0) {
-    // publish: the CTA's peer stores happen-before the barrier, thread 0's system-scope fence is cumulative over them;
-    // then count the CTA; the last one signals every rank
+    // publish: the CTA's peer stores happen-before the barrier; thread 0's system-scope fence is cumulative over them
+    // and orders them before its relaxed signals (fence-based release).  Every CTA signals every rank directly with
+    // its share of kArrivalsPerLaunch (the shares of a launch add up to exactly that), so a launch costs each CTA ONE
+    // fence round trip: no CTA counting, no second fence in a last CTA, no release (= another fence) per signal.
     __syncthreads();
     if (tid == 0) {
       __threadfence_system();
-      const unsigned old = atomicAdd(p.local_count, 1u);
-      if (old == gridDim.x - 1) {
-        *p.local_count = 0u;                         // ready for the next step
-        __threadfence_system();
-        for (int pr = 0; pr < p.nranks; ++pr)
-          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.done_peer[pr]) : "memory");
-      }
+      const unsigned inc = arrival_share(blockIdx.x, gridDim.x);
+      for (int pr = 0; pr < p.nranks; ++pr)
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p.done_peer[pr]), "r"(inc) : "memory");
     }
   }
   stamp(p, 5);
@@ -920,7 +976,7 @@ static int gemv_entry(const void* x, const qeft_gemv_part_t* parts, int nparts, 
   if (r < 0 || r % 32 != 0 || r >= K) return QEFT_E_SHAPE;
   if (r > 0 && ow_layout != QEFT_OW_PLAIN && ow_layout != QEFT_OW_INTERLEAVED) return QEFT_E_DTYPE;
   if (r == 0) ow_layout = QEFT_OW_NONE;
-  if (!check_align16(x)) return QEFT_E_ALIGN;
+  if (!check_align16(x) || (x_gather && !check_align16(x_gather))) return QEFT_E_ALIGN;
   GemvParams prm = {};
   int total_q = 0;
   for (int i = 0; i < nparts; ++i) {
@@ -954,7 +1010,7 @@ static int gemv_entry(const void* x, const qeft_gemv_part_t* parts, int nparts, 
   prm.nou = cdiv(r, 64);
   prm.xstride = 128 * prm.nsteps + 32;
   if (gat) {
-    if (gat->nranks < 1 || gat->nranks > QEFT_MAX_RANKS || !gat->local_count || !gat->epoch) return QEFT_E_SHAPE;
+    if (gat->nranks < 1 || gat->nranks > QEFT_MAX_RANKS || !gat->epoch) return QEFT_E_SHAPE;
     prm.nranks = gat->nranks;
     prm.y_ld = gat->y_ld;
     for (int pr = 0; pr < gat->nranks; ++pr) {
@@ -967,6 +1023,8 @@ static int gemv_entry(const void* x, const qeft_gemv_part_t* parts, int nparts, 
     }
     prm.local_count = gat->local_count;
     prm.wait_flag = gat->wait_flag;
+    static const int gridwait_env = getenv("QEFT_GATHER_GRIDWAIT") ? atoi(getenv("QEFT_GATHER_GRIDWAIT")) : 0;
+    prm.flag_only = (gat->wait_flag != nullptr && (flags & QEFT_F_PDL) && !gridwait_env) ? 1 : 0;
     prm.epoch = gat->epoch;
   }   // the int4 steps' columns (dead columns of the last step staged as zeros)
   cudaStream_t st = static_cast<cudaStream_t>(stream);

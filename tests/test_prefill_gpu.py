@@ -31,7 +31,7 @@ def test_gemm_gather_single_rank_writes_pitched_columns():
     torch.cuda.synchronize()
     assert torch.equal(full[:, 256:512], want)
     assert torch.all(full[:, :256] == 7.0) and torch.all(full[:, 512:] == 7.0)
-    assert flags.tolist() == [1, 0]                      # arrival counter signalled once, CTA counter reset
+    assert flags.tolist() == [65536, 0]                  # the CTAs' shares add up to QEFT_ARRIVALS_PER_LAUNCH
     ref = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], L["bias"])
     err = np.max(np.abs(want.cpu().numpy().astype(np.float64) - ref.astype(np.float64))) / np.max(np.abs(ref.astype(np.float64)))
     assert err <= 1e-3
@@ -46,7 +46,7 @@ def test_gemm_gather_single_rank_writes_pitched_columns():
     g2.epoch = epoch.data_ptr()
     qeft_cuda.gemm_w4_gather(d(x), T["qweight"], T["scales"], T["scaled_zeros"], T["oweight"], T["bias"], g2)
     torch.cuda.synchronize()
-    assert torch.equal(full[:, :256], want) and flags2.tolist() == [1, 0]
+    assert torch.equal(full[:, :256], want) and flags2.tolist() == [65536, 0]
 
 
 def test_prefill_stack_single_gpu_matches_per_layer_gemm():
