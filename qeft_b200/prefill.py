@@ -88,9 +88,13 @@ class PackedPrefillStack:
         self.y_full = [{n: torch.empty((M, self.full[n]), dtype=torch.float16, device=self.device) for n in NAMES}
                        for _ in range(2)]
 
-    def enable_fused_gather(self, process_group, multicast=True):
+    def enable_fused_gather(self, process_group, multicast=None):
         """``multicast``: store each tile once to the NVLS multicast mapping of the gathered buffer (the NVSwitch
-        replicates it to all ranks) when the symmetric allocation has one; else one store per rank."""
+        replicates it to all ranks) when the symmetric allocation has one; else one store per rank.  Default: only
+        from 8 ranks up (measured on B200: 10 % faster than per-rank stores at 8 ranks, 6-8 % slower at 2 and 4,
+        where the copy that comes back to the sender costs more than the saved egress)."""
+        if multicast is None:
+            multicast = self.world >= 8
         import torch.distributed._symmetric_memory as symm_mem
         P, M = self.world, self.M
         nlaunch = 7 * self.nlayers
