@@ -6,8 +6,9 @@
 N = 1 workload (BASELINE.json configs[1]): Llama-2-7B-shape, w4 g128 r128, batch 1 decode: one "step" is
 one token through the 224 packed QuantLinear GEMVs of the 32 decoder blocks (3.701 GB of algorithmic bytes,
 far larger than the 126 MB L2, so every step streams its weights from HBM).
-N > 1 workload (configs[4]): Llama-2-70B shapes, every linear column-sharded over the N ranks, NCCL
-all-gather of each projection group's output over NVLink; strong scaling (total work fixed).
+N > 1 workload (configs[4]): Llama-2-70B shapes, every linear column-sharded over the N ranks, the all-gather of
+each launch's output fused into the GEMV epilogue over NVLink (`--gather nccl`: one NCCL all-gather per launch);
+strong scaling (total work fixed).  The line also carries `prefill_sharded`: the same shapes at M = 2048 tokens.
 
 `--impl reference`: the reference has no CPU implementation of this path (every forward calls its CUDA
 extension).  When `oracle/_ref/qeft_cuda_ref.so` (the reference's own kernels, recompiled for sm_100a by
@@ -301,10 +302,16 @@ def run_ours(args):
     model = args.model or ("7b" if world == 1 else "70b")
     stack = PackedDecoderStack(model, layers=args.layers, fused=not args.no_fused, pdl=not args.no_pdl,
                                shard=(rank, world), batch=args.batch, device=f"cuda:{local}", fast_synth=True)
+    gather_mode = args.gather
     if world > 1:
-        if args.gather == "fused":
-            stack.enable_fused_gather(dist.group.WORLD)
-        else:
+        if gather_mode == "fused":
+            try:
+                stack.enable_fused_gather(dist.group.WORLD)
+            except Exception as e:  # noqa: BLE001  (no peer-mapped symmetric memory on this box: NCCL still works)
+                print(f"bench.py: fused gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+                gather_mode = "nccl"
+                stack.fused_gather = None
+        if gather_mode == "nccl":
             stack.enable_allgather(dist.group.WORLD)
     if not args.no_graph:
         stack.capture()
@@ -368,6 +375,9 @@ def run_ours(args):
         del stack
         torch.cuda.empty_cache()
         extra["prefill_finetune"] = bench_gemm(model)
+        if model == "7b":
+            # configs[3]: the 13B shapes of the fine-tuning step (fwd + dX + dOW per linear, M = 2048)
+            extra["finetune_13b"] = bench_gemm("13b")
         stack = None
     if not args.no_gemm and world > 1:
         # configs[4], prefill half: the same shapes, M = 2048 tokens, every linear column-sharded; all three exchanges
@@ -393,7 +403,7 @@ def run_ours(args):
                 "workload": (f"llama2-{model} decode b{args.batch}: {workload_layers} decoder blocks x 7 packed QuantLinear "
                              f"(w4 g128 r128) = {launches_per_step} GEMV launches/token"
                              + (f", column-sharded over {world} ranks, all-gather "
-                                + ("fused into the GEMV epilogue (peer stores over NVLink)" if args.gather == "fused" else "by NCCL")
+                                + ("fused into the GEMV epilogue (peer stores over NVLink)" if gather_mode == "fused" else "by NCCL")
                                 if world > 1 else "")),
                 "algorithmic_bytes_per_step": int(nbytes_all), "l2_policy": "inputs larger than L2 (3.7 GB of weights streamed per step)",
                 "cuda_graph": workload_graph, "fused_qkv_gateup": workload_fused, "pdl": workload_pdl,
@@ -523,7 +533,11 @@ def bench_gemm(model, M=2048, iters=10):
         tf = timeit(lambda: qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, out=y, pdl=False))
         tb = timeit(lambda: qeft_cuda.gemm_w4_dx(dy, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], K, out=dx, pdl=False))
         tw = timeit(lambda: qeft_cuda.dow(dy, xo, 128, out=dow))
-        out["shapes"].append({"name": name, "N": N, "K": K,
+        xb, owb = x.bfloat16(), t["oweight"].bfloat16()
+        yb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        tfb = timeit(lambda: qeft_cuda.gemm_w4(xb, t["qweight"], t["scales"], t["scaled_zeros"], owb, None, out=yb, pdl=False))
+        del xb, owb, yb
+        out["shapes"].append({"name": name, "N": N, "K": K, "fwd_bf16_TFLOPs": flops / tfb / 1e12,
                               "fwd_TFLOPs": flops / tf / 1e12, "fwd_frac": flops / tf / 1e12 / tpeak,
                               "dx_TFLOPs": flops / tb / 1e12, "dx_frac": flops / tb / 1e12 / tpeak,
                               "dow_us": tw * 1e6,
