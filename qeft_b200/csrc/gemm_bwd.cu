@@ -41,6 +41,7 @@ struct DxParams {
   const __half* ow;        // [N, r] or null
   __half* dx;              // [M, K]
   int M, N, K, r, G;
+  int tbc;                 // 128-token blocks per CTA: 2, or 1 where that fills the SMs' waves better
 };
 
 template <bool BF16>
@@ -56,10 +57,10 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
   auto empty = [&](int s) { return bar0 + 8 * (kDxStages + s); };
   const uint32_t acc_full = bar0 + 8 * (2 * kDxStages);
 
-  const int tok0 = blockIdx.x * (128 * kDxTB);
+  const int tok0 = blockIdx.x * (128 * p.tbc);
   const int kf0 = blockIdx.y * kDxBF;
   const int nkb = p.N / kDxBK;
-  const int ntb = (p.M - tok0) > 128 ? 2 : 1;       // token blocks with at least one live token
+  const int ntb = (p.M - tok0) > 128 ? p.tbc : 1;   // token blocks with at least one live token
 
   if (tid == 0) {
     for (int s = 0; s < kDxStages; ++s) { mbar_init(full(s), 1 + kDxDequantWarps); mbar_init(empty(s), 1); }
@@ -384,13 +385,22 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
   prm.ow = r > 0 ? static_cast<const __half*>(oweight) : nullptr;
   prm.dx = static_cast<__half*>(dx);
   prm.M = M; prm.N = N; prm.K = K; prm.r = r; prm.G = G;
+  // Tile = 256 features x 2 x 128 tokens, one CTA per SM.  QEFT_DX_TBC=1 halves the token extent of a tile (more,
+  // smaller tiles for grids that leave a nearly empty last wave, e.g. 13B K = 5120: 160 tiles on 148 SMs).  Measured on
+  // B200 it loses everywhere (5120 x 5120: 272 us against 211; 4096 x 4096: 150 against 92): a 1-block tile costs
+  // 0.8-1.0 of a 2-block tile, i.e. the kernel is bound by producing the dequantised B tile (the same work for both),
+  // not by the MMAs or their operand traffic.  Kept as an experiment switch only.
+  {
+    static const int tbc_env = getenv("QEFT_DX_TBC") ? atoi(getenv("QEFT_DX_TBC")) : 0;
+    prm.tbc = tbc_env == 1 ? 1 : 2;
+  }
   const size_t smem = (size_t)kDxStages * kDxStageBytes + 1024;
   static bool done[2][64] = {};
   const bool bf = dtype == QEFT_DT_BF16;
   st = bf ? set_smem_once(gemm_w4_dx_kernel<true>, smem, done[1]) : set_smem_once(gemm_w4_dx_kernel<false>, smem, done[0]);
   if (st != QEFT_OK) return st;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cdiv(M, 128 * kDxTB), (unsigned)cdiv(K, kDxBF));
+  cfg.gridDim = dim3((unsigned)cdiv(M, 128 * prm.tbc), (unsigned)cdiv(K, kDxBF));
   cfg.blockDim = dim3(kDxThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
