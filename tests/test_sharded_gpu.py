@@ -135,3 +135,29 @@ def test_prefill_fused_gather_equals_nccl_and_unsharded():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_launch_on_a_device_that_is_not_current():
+    """The reference launches on the legacy default stream of the current device; this wrapper launches on the
+    tensors' device whatever the current one is (the device guard is skipped only when they coincide)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+
+    import oracle
+    from qeft_b200 import _lib, qeft_cuda
+    N, K, r, m = 256, 512, 128, 1
+    L = oracle.synth_layer(N, K, r=r, G=128, seed=3)
+    x = np.random.default_rng(0).standard_normal((m, K)).astype(np.float16)
+    want = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], None)
+    torch.cuda.set_device(0)
+    d1 = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to("cuda:1")  # noqa: E731
+    y = qeft_cuda.gemv_w4(d1(x), d1(L["qweight"]), d1(L["scales"]), d1(L["scaled_zeros"]), d1(L["oweight_interleaved"]),
+                          m, N, K, 128, ow_layout=_lib.OW_INTERLEAVED)
+    xm = np.random.default_rng(1).standard_normal((40, K)).astype(np.float16)
+    ym = qeft_cuda.gemm_w4(d1(xm), d1(L["qweight"]), d1(L["scales"]), d1(L["scaled_zeros"]), d1(L["oweight"]), None)
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0 and y.device.index == 1 and ym.device.index == 1
+    rel = lambda a, b: float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / np.max(np.abs(b.astype(np.float64))))  # noqa: E731
+    assert rel(y.cpu().numpy(), want) <= 1e-3
+    assert rel(ym.cpu().numpy(), oracle.forward(xm, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], None)) <= 1e-3
