@@ -55,6 +55,11 @@ __device__ __forceinline__ unsigned arrival_share(unsigned i, unsigned n) {
   return (unsigned)(((unsigned long long)kArrivalsPerLaunch * (i + 1)) / n) - (unsigned)(((unsigned long long)kArrivalsPerLaunch * i) / n);
 }
 
+// Release side of the arrival-counter protocol.  __threadfence_system() is a SEQUENTIALLY CONSISTENT fence
+// (MEMBAR.SC.SYS); ordering earlier stores before a later relaxed signal needs only acquire-release (MEMBAR.ALL.SYS),
+// which does not have to be ordered against every other CTA's fence.
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- int4 -> fp16 ------------------------------------------------------------------------

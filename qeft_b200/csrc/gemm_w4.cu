@@ -367,7 +367,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
     // publish (same protocol as the decode GEMV): the CTA's stores happen-before the barrier above, this thread's
     // system-scope fence is cumulative over them and orders them before its relaxed signals; every CTA signals its
     // share of kArrivalsPerLaunch to every rank
-    __threadfence_system();
+    fence_acq_rel_sys();
     const unsigned inc = arrival_share(blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
     for (int pr = 0; pr < p.nranks; ++pr)
       asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p.done_peer[pr]), "r"(inc) : "memory");

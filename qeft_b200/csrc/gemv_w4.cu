@@ -828,7 +828,7 @@ gemv_w4_kernel(const GemvParams p) {
     // fence round trip: no CTA counting, no second fence in a last CTA, no release (= another fence) per signal.
     __syncthreads();
     if (tid == 0) {
-      __threadfence_system();
+      fence_acq_rel_sys();
       const unsigned inc = arrival_share(blockIdx.x, gridDim.x);
       for (int pr = 0; pr < p.nranks; ++pr)
         asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p.done_peer[pr]), "r"(inc) : "memory");
