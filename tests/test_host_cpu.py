@@ -45,6 +45,42 @@ def test_argument_validation_without_a_gpu():
     assert lib.qeft_gemv_w4(misaligned, dummy, dummy, dummy, None, 0, None, None, dummy, 1, 64, 128, 0, 128, 0, None) == -5
 
 
+def test_gather_entries_validate_before_touching_the_device():
+    """qeft_gemm_w4_gather / qeft_gemv_w4_multi_gather: descriptor rules are checked before any CUDA call."""
+    lib = _lib.load()
+    dummy = ctypes.c_void_p(16)
+    gemm = lambda g, N=256, y_ld=512: lib.qeft_gemm_w4_gather(  # noqa: E731
+        dummy, dummy, dummy, dummy, None, None, 64, N, 128, 0, 128, _lib.DT_F16, 0, g, None)
+    assert gemm(None) == -1                                   # no descriptor
+    g = _lib.Gather()
+    g.nranks, g.y_ld = 0, 512
+    g.epoch = 16
+    assert gemm(ctypes.byref(g)) == -2                        # ranks outside 1..QEFT_MAX_RANKS
+    g.nranks = _lib.MAX_RANKS + 1
+    assert gemm(ctypes.byref(g)) == -2
+    g.nranks, g.y_ld = 2, 128
+    assert gemm(ctypes.byref(g)) == -2                        # gathered row pitch smaller than this rank's N
+    g.y_ld = 512
+    g.y_peer[0][0] = 16
+    g.done_peer[0] = 16
+    assert gemm(ctypes.byref(g)) == -1                        # rank 1 has no buffer / counter
+    g.y_peer[1][0] = 24
+    g.done_peer[1] = 16
+    assert gemm(ctypes.byref(g)) == -5                        # misaligned peer buffer
+    g.y_peer[1][0] = 32
+    g.epoch = None
+    assert gemm(ctypes.byref(g)) == -2                        # the step counter is mandatory
+    assert gemm(ctypes.byref(g), N=200) == -2                 # N % 128 (checked before the descriptor)
+    part = (_lib.GemvPart * 1)()
+    part[0] = _lib.GemvPart(16, 16, 16, None, None, None, 64)
+    g.epoch = 16
+    gemv = lambda gp, xg=None: lib.qeft_gemv_w4_multi_gather(dummy, part, 1, 0, xg, 1, 128, 0, 128, 0, gp, None)  # noqa: E731
+    assert gemv(None) == -1
+    assert gemv(ctypes.byref(g), ctypes.c_void_p(8)) == -5    # x_gather must be 16-byte aligned
+    g.nranks = 9
+    assert gemv(ctypes.byref(g)) == -2
+
+
 def test_no_cpu_fallback():
     x = torch.zeros(1, 128, dtype=torch.float16)
     qw = torch.zeros(16, 128, dtype=torch.int16)
