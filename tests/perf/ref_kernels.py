@@ -1,7 +1,7 @@
 """The reference's own kernels (oracle/_ref/qeft_cuda_ref.so, unmodified, recompiled for sm_100a) timed beside ours
 on the same B200, same packed tensors, same shapes.
 
-    python tools/ref_kernels.py [--iters 100]
+    python tests/perf/ref_kernels.py [--iters 100]
 One JSON line per shape: decode GEMV (m = 1) and prefill GEMM (M = 2048).  Both sides are timed as plain launches on
 the default stream with CUDA events (the reference launches on the legacy default stream and cannot be graph-captured);
 weights rotate through > 3x L2 bytes.  `ours_chain_us` is our GEMV inside a CUDA graph with PDL (how decode.py runs it).
@@ -13,9 +13,9 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import build_ref  # noqa: E402  (measurement tool, not product code)
+from oracle import build_ref  # noqa: E402  (under tests/: the only tree besides bench.py / smoke() that may touch oracle/)
 from qeft_b200 import _lib, qeft_cuda  # noqa: E402
 from qeft_b200.synth import synth_tensors  # noqa: E402
 

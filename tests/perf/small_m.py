@@ -1,7 +1,7 @@
 """Small token counts (8 <= M <= 256): the tcgen05 GEMM against ceil(M / 8) decode-GEMV launches and the reference's
 gemm_4bit (+ outlier F.linear), per Llama-2-7B layer shape.  Decides the host-side dispatch in QuantLinear.forward.
 
-    python tools/small_m.py
+    python tests/perf/small_m.py
 """
 import json
 import os
@@ -9,9 +9,9 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import build_ref  # noqa: E402  (measurement tool)
+from oracle import build_ref  # noqa: E402  (under tests/: the only tree besides bench.py / smoke() that may touch oracle/)
 from qeft_b200 import _lib, qeft_cuda  # noqa: E402
 from qeft_b200.synth import synth_tensors  # noqa: E402
 
