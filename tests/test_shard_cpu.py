@@ -48,6 +48,53 @@ def _worker(rank, world, port, N, K, r, q):
         dist.destroy_process_group()
 
 
+def _prefill_worker(rank, world, port, N, K, r, M, q):
+    """The prefill exchange's layout (prefill.py): local [M, N/P] slab -> all-gather to [P, M, N/P] -> permuting copy to
+    [M, N]; and the fused variant's addressing (row pitch N, column offset rank * N/P) gives the same matrix."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = oracle.synth_layer(N, K, r=r, seed=5)
+        t = {k: torch.from_numpy(np.ascontiguousarray(L[k])) for k in
+             ("qweight", "scales", "scaled_zeros", "oweight", "oweight_interleaved")}
+        sh = shard_layer_tensors(t, rank, world)                 # 128-row multiples, as the tensor-core tiles need
+        x = np.random.default_rng(1).standard_normal((M, K)).astype(np.float16)
+        y_local = oracle.forward(x, sh["qweight"].numpy(), sh["scales"].numpy(), sh["scaled_zeros"].numpy(),
+                                 sh["oweight"].numpy(), None)
+        assert y_local.shape == (M, N // world)
+        stage = torch.empty((world, M, (N // world) * 2), dtype=torch.uint8)
+        dist.all_gather_into_tensor(stage.view(-1), torch.from_numpy(np.ascontiguousarray(y_local).view(np.uint8).copy()).view(-1))
+        y_full = torch.empty((M, N * 2), dtype=torch.uint8)
+        y_full.view(M, world, -1).copy_(stage.permute(1, 0, 2))          # the copy enable_allgather's step() makes
+        want = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], None)
+        ok = np.array_equal(y_full.numpy().view(np.uint16), want.view(np.uint16))
+        # fused addressing: element (tok, f) of the slab lands at tok * y_ld + rank * N/P + f of every rank's buffer
+        flat = np.zeros(M * N, dtype=np.uint16)
+        lo = rank * (N // world)
+        idx = (np.arange(M)[:, None] * N + lo + np.arange(N // world)[None, :]).reshape(-1)
+        flat[idx] = y_local.view(np.uint16).reshape(-1)
+        ok = ok and np.array_equal(flat.reshape(M, N)[:, lo:lo + N // world], want.view(np.uint16)[:, lo:lo + N // world])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_prefill_exchange_layout():
+    world, N, K, r, M = 2, 256, 256, 64, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_prefill_worker, args=(rank, world, port, N, K, r, M, q)) for rank in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 @pytest.mark.timeout(120)
 def test_two_rank_shards_reproduce_the_unsharded_layer():
     world, N, K, r = 2, 64, 256, 64
