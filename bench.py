@@ -345,7 +345,7 @@ def run_ours(args):
     # ---- end to end: pinned host activations in, result back on the host, every step ------------------
     xh = torch.randn(stack.x_h.shape).half().pin_memory()
     xf = torch.randn(stack.x_f.shape).half().pin_memory()
-    yh = torch.empty(stack.out[-1]["down"].shape, dtype=torch.float16).pin_memory()
+    yh = torch.empty(stack.result().shape, dtype=torch.float16).pin_memory()
     for _ in range(3):
         stack.step_from_host(xh, xf, yh)
     barrier()

@@ -112,7 +112,12 @@ QEFT_API int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, in
  * `*epoch * nranks * QEFT_ARRIVALS_PER_LAUNCH` before it reads its input; with QEFT_F_PDL that counter is the ONLY
  * ordering between the two launches (no grid-completion wait), so the chain never pays a kernel boundary.
  * `epoch` is a device-resident step counter the caller increments once per decode step (graph-replay friendly).
- * `local_count` is unused (kept for layout compatibility).  x_gather, when given, must be 16-byte aligned.
+ * `local_count` is reserved.  x_gather, when given, must be 16-byte aligned.
+ * A launch with `wait_flag` reads x through L2 (coherent loads), never through the read-only path.
+ * Contract of QEFT_F_PDL for every entry point: only x (and y as a reused buffer) are ordered after the previous
+ * kernel in the stream; the packed tensors (qweight, scales, scaled_zeros, oweight, bias) are prefetched BEFORE the
+ * dependency wait and must not be written by the kernel immediately before the launch (launch without the flag
+ * after a pack / dequant / cast that produces them).
  */
 #define QEFT_ARRIVALS_PER_LAUNCH 65536u
 #define QEFT_MAX_RANKS 8
@@ -121,7 +126,7 @@ typedef struct {
   int y_ld;                                            /* elements between batch rows of the gathered buffers */
   void* y_peer[QEFT_MAX_RANKS][QEFT_GEMV_MAX_PARTS];   /* rank p's buffer for part i, offset to THIS rank's columns */
   uint32_t* done_peer[QEFT_MAX_RANKS];                 /* rank p's arrival counter of this launch */
-  uint32_t* local_count;
+  uint32_t* local_count;                               /* reserved, must be NULL (never read) */
   const uint32_t* wait_flag;                           /* local arrival counter of the launch depended on, or NULL */
   const uint32_t* epoch;
   /* qeft_gemm_w4_gather only, optional: the MULTICAST mapping (NVLS; torch symmetric memory's multicast_ptr) of the
@@ -133,6 +138,48 @@ typedef struct {
 QEFT_API int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* parts, int nparts, int ow_layout,
                               const int32_t* x_gather, int m, int K, int r, int G, unsigned flags,
                               const qeft_gather_t* gather, qeft_stream_t stream);
+
+/*
+ * Blocks `stream` (a one-thread kernel) until the launch whose local arrival counter is `arrival_counter` has received
+ * every rank's slice: for consumers of a gathered buffer that are not chain kernels (a copy to the host).
+ */
+QEFT_API int qeft_gather_wait(const uint32_t* arrival_counter, const uint32_t* epoch, int nranks, qeft_stream_t stream);
+
+/*
+ * Decode programs: a chain of dependent decode GEMVs (one decoder block, or a whole token) as ONE cooperative launch
+ * of a persistent kernel (csrc/decode_w4.cu).  No reference counterpart as an entry point: it replaces the
+ * reference's sequence of one `gemv_4bit_qeft` launch per projection (qeft/qlinear.py:251-263, driven per token by
+ * qeft/main.py:356-366) plus, optionally, the elementwise glue between them.
+ * A stage is what qeft_gemv_w4_multi computes (batch m <= 2, oweight in the PLAIN [N, r] layout), with
+ *   norm_weight != NULL : x is first RMS-normalised like HF LlamaRMSNorm / the reference's FT layernorm
+ *                         (qeft/kernel/layernorm/layernorm.cu:25-51): weight * (x * rsqrt(mean(x^2) + eps)).to(fp16)
+ *   QEFT_EPI_SWIGLU     : parts = {gate, up} (equal N); writes y0 = silu(fp16(gate)) * fp16(up)  (parts[1].y unused)
+ *   QEFT_EPI_RESIDUAL   : one part; writes y = residual + fp16(linear)
+ * Stage i+1 may read what stage i wrote (a gpu-scope barrier separates consecutive stages of a launch).
+ * qeft_decode_program_run launches stages [begin, end) on `stream`; the program owns only its descriptor copy and
+ * its barrier words, never the tensors.  One run of a program at a time (runs on one stream are ordered).
+ */
+#define QEFT_EPI_NONE 0
+#define QEFT_EPI_SWIGLU 1
+#define QEFT_EPI_RESIDUAL 2
+typedef struct {
+  qeft_gemv_part_t parts[QEFT_GEMV_MAX_PARTS];
+  int nparts;
+  int K, r, G;
+  const void* x;               /* fp16 [m, K] */
+  const int32_t* x_gather;     /* int32 [K] or NULL (o_proj reorder, qeft/qlinear.py:273-275) */
+  const void* norm_weight;     /* fp16 [K] or NULL */
+  float norm_eps;
+  int epilogue;                /* QEFT_EPI_* */
+  const void* residual;        /* fp16 [m, N] (QEFT_EPI_RESIDUAL) */
+} qeft_decode_stage_t;
+typedef struct qeft_decode_program qeft_decode_program_t;
+QEFT_API int qeft_decode_program_create(const qeft_decode_stage_t* stages, int nstages, int m,
+                                        qeft_decode_program_t** out);
+QEFT_API int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_begin, int stage_end, unsigned flags,
+                                     qeft_stream_t stream);
+QEFT_API int qeft_decode_program_num_stages(const qeft_decode_program_t* prog);
+QEFT_API int qeft_decode_program_destroy(qeft_decode_program_t* prog);
 
 /*
  * Prefill / fine-tune GEMM:  y[M, N] = x[M, K] . Wdense^T (+ bias)  on tcgen05 tensor cores.

@@ -128,6 +128,28 @@ def build(verbose: bool = True) -> str | None:
     return MODULE
 
 
+# The reference's own PYTHON of the path (qeft/qlinear.py, qeft/reorder.py), staged UNMODIFIED next to the compiled
+# kernels so that the drop-in test (tests/test_reference_module_gpu.py) can run the reference's QuantLinear against this
+# repo's `qeft_cuda` shim on the GPU box, where /root/reference does not exist.  baseline/_ref/ is git-ignored (the
+# files never enter the history) and travels with gpurun, like oracle/_ref/.
+PY_STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+PY_FILES = ["qeft/__init__.py", "qeft/qlinear.py", "qeft/reorder.py"]
+
+
+def stage_reference_python() -> str | None:
+    """Copy the reference's qlinear.py / reorder.py as they are into baseline/_ref/qeft/ (only where /root/reference
+    exists); returns the directory to put on sys.path, or None when neither the reference nor a staged copy exists."""
+    have_ref = all(os.path.exists(os.path.join(REF, f)) for f in PY_FILES)
+    if have_ref:
+        for f in PY_FILES:
+            dst = os.path.join(PY_STAGE, f)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            src = os.path.join(REF, f)
+            if not os.path.exists(dst) or open(src, "rb").read() != open(dst, "rb").read():
+                shutil.copyfile(src, dst)
+    return PY_STAGE if all(os.path.exists(os.path.join(PY_STAGE, f)) for f in PY_FILES) else None
+
+
 def load():
     """Import oracle/_ref/qeft_cuda_ref.so (prebuilt); None if it is not there.  Never builds."""
     if not os.path.exists(MODULE):

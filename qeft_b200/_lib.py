@@ -32,6 +32,16 @@ class Gather(C.Structure):
                 ("y_mc", C.c_void_p * GEMV_MAX_PARTS)]
 
 
+EPI_NONE, EPI_SWIGLU, EPI_RESIDUAL = 0, 1, 2
+
+
+class DecodeStage(C.Structure):
+    """qeft_decode_stage_t (include/qeft_b200.h)."""
+    _fields_ = [("parts", GemvPart * GEMV_MAX_PARTS), ("nparts", C.c_int), ("K", C.c_int), ("r", C.c_int),
+                ("G", C.c_int), ("x", C.c_void_p), ("x_gather", C.c_void_p), ("norm_weight", C.c_void_p),
+                ("norm_eps", C.c_float), ("epilogue", C.c_int), ("residual", C.c_void_p)]
+
+
 _vp, _i, _u = C.c_void_p, C.c_int, C.c_uint
 # name -> (restype, argtypes): every symbol include/qeft_b200.h declares
 SIGNATURES = {
@@ -42,6 +52,11 @@ SIGNATURES = {
     "qeft_gemv_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemv_w4_multi": (_i, [_vp, C.POINTER(GemvPart), _i, _i, _vp, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemv_w4_multi_gather": (_i, [_vp, C.POINTER(GemvPart), _i, _i, _vp, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),
+    "qeft_gather_wait": (_i, [_vp, _vp, _i, _vp]),
+    "qeft_decode_program_create": (_i, [C.POINTER(DecodeStage), _i, _i, C.POINTER(C.c_void_p)]),
+    "qeft_decode_program_run": (_i, [_vp, _i, _i, _u, _vp]),
+    "qeft_decode_program_num_stages": (_i, [_vp]),
+    "qeft_decode_program_destroy": (_i, [_vp]),
     "qeft_gemm_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemm_w4_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),
     "qeft_gemm_w4_dx": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),

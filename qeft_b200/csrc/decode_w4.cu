@@ -1,0 +1,936 @@
+// Persistent multi-stage decode kernel for the packed QEFT QuantLinear (sm_100a): "decode programs".
+//
+// Replaces the reference's one-kernel-per-projection decode path (qeft/qlinear.py:251-263 ->
+// gemv_kernel_qeft, qeft/kernel/quantization_new/gemv/gemv_cuda_qeft.cu:75-222, launcher :392-513) for a whole
+// chain of dependent GEMVs: one decoder block (qkv -> o -> gate/up -> down) or a whole token (4 x layers stages)
+// is ONE cooperative launch.  A stage is what qeft_gemv_w4_multi computes (up to 4 projections sharing x, fp16
+// outlier columns, bias, the o_proj gather of qlinear.py:273-275), optionally with the elementwise glue of a
+// Llama block folded in (RMSNorm on the way in -- kernel/layernorm/layernorm.cu:25-51 --, SiLU(gate)*up or a
+// residual add on the way out).
+//
+// Why (round-1 measurements): a decode token is 128 dependent launches of 10-50 MB; each launch
+// paid ~4.5 us of fixed serial cost (kernel boundary, x staging, ring fill, reduce) against 1.5-7 us of DRAM time,
+// and the old kernel needed ~155 warp instructions per KB of weights, i.e. it could not consume faster than HBM
+// delivers, so nothing was ever caught up.  Here:
+//   * one CTA of 16 warps per SM stays resident for the whole program; stage boundaries are a gpu-scope arrival
+//     counter (red.release.gpu / ld.acquire.gpu), never a kernel boundary;
+//   * the weight stream never stops at a boundary: every warp owns a private ring of D 1-KB units filled with
+//     cp.async (LDGSTS, 16 B per lane, placed so that the consumer's LDS.128 are conflict-free and lane-private),
+//     and the ring's prefetch cursor runs ahead through the NEXT stages' weights (they never depend on x) while
+//     the warp waits for the barrier and for x: ~170 KB per SM stay in flight across the boundary;
+//   * the inner loop is ~45 warp instructions per KB: int8 tensor-core dot products (IMMA.16832, two AND masks per
+//     packed word, exact s32 accumulation) against x held as four signed-byte digits of a 30-bit block fixed point
+//     with ONE exponent per activation row (so the digit weights leave the loop), scales applied once per
+//     128-column group in fp32;
+//   * x is converted once per stage and CTA from L2 (redundantly per CTA: one L2 round trip, no second
+//     publish/subscribe hop).
+//
+// Work split: the stage's qweight rows (4 output rows each) are split evenly over the CTAs (balance to one
+// qweight row); a CTA cuts its rows into 16-row tiles and each tile into units of one 128-column int4 step
+// (1 KB) or 32 fp16 outlier columns (1 KB); the CTA's (tile, unit) sequence is split into 16 contiguous runs,
+// one per warp.  Partial sums meet in shared memory in a fixed order (deterministic results).
+#include "common.cuh"
+
+#include <stdlib.h>
+
+#include <vector>
+
+namespace qeft {
+
+constexpr int kDWarps = 16;
+constexpr int kDThreads = kDWarps * 32;
+constexpr int kSlotScale = 1024;              // byte offset of the unit's scales (32 B) and scaled zeros (32 B)
+constexpr int kSlot = 1088;                   // bytes per ring slot
+constexpr size_t kDSmemMax = 227 * 1024;
+
+struct DecPart {
+  const uint8_t* qw;
+  const __half* scales;
+  const __half* szeros;
+  const __half* ow;       // plain [N, r]
+  const __half* bias;
+  __half* y;              // [m, N]
+  int N;
+  int q_begin;            // first qweight row of this part in the stage-wide numbering (plain stages)
+};
+
+struct DecStage {
+  DecPart part[QEFT_GEMV_MAX_PARTS];
+  const __half* x;            // [m, K]
+  const int32_t* gather;      // [K] or null: x[:, gather[k]] is column k
+  const __half* norm_w;       // [K] or null: RMSNorm weight applied to x on the way in
+  const __half* residual;     // [m, N] or null: added to the (fp16-rounded) result of part 0
+  float norm_eps;
+  int nparts;
+  int K, r;
+  int g128;                   // G / 128, 0 for per-channel scales
+  int nsteps, nchunks, nou;   // int4 steps, live 32-column chunks, outlier units (r / 32)
+  int total_q;                // qweight rows of all parts
+  int epilogue;               // QEFT_EPI_*
+};
+
+struct DecLayout {            // shared-memory carve-up (bytes from the start of dynamic shared memory)
+  int xdig, xsum, xo, part, misc;
+  int max_touch;              // tiles a warp's run can touch
+  unsigned long long* stamps; // debug (QEFT_DECODE_STAMPS): [stage][4 CTAs][4] globaltimer values, or null
+};
+
+__device__ __forceinline__ void dec_stamp(const DecLayout& L, int s, int i) {
+  if (L.stamps && threadIdx.x == 0) {
+    const int c = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : (blockIdx.x == gridDim.x / 2 ? 2 : (blockIdx.x == 1 ? 3 : -1)));
+    if (c >= 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      L.stamps[((size_t)s * 4 + c) * 4 + i] = t;
+    }
+  }
+}
+
+// ---- small PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t d_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d_cp16(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void d_cp8(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void d_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void d_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 d_lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+  return r;
+}
+// predicated: lanes with p == 0 do not touch shared memory and keep the previous register contents
+__device__ __forceinline__ void d_lds128_if(uint4& r, uint32_t a, int p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+               : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "r"(a), "r"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t d_lds32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ float d_ldsf(uint32_t a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ void d_sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t d_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// coherent (L2) loads for data written by other CTAs of the same launch
+__device__ __forceinline__ uint4 d_ldcg128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ unsigned short d_ldcg16(const void* p) {
+  unsigned short r;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void d_imma(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void d_imma0(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+struct DecRun { int qa, nq, U, ns, u0, u1, ntiles; };
+
+// this CTA's qweight rows of a stage and one warp's run of (tile, unit) pairs
+__device__ __forceinline__ DecRun dec_run(const DecStage* S, int cta, int ncta, int warp) {
+  DecRun R;
+  const int al = S->epilogue == QEFT_EPI_SWIGLU ? 2 : 1;     // SwiGLU: gate / up qweight rows alternate, CTAs own pairs
+  const long Qa = S->total_q / al;
+  R.qa = al * (int)((Qa * cta) / ncta);
+  R.nq = al * (int)((Qa * (cta + 1)) / ncta) - R.qa;
+  R.ntiles = (R.nq + 3) >> 2;
+  R.ns = S->nsteps;
+  R.U = R.ns + S->nou;
+  const int TU = R.ntiles * R.U;
+  R.u0 = (warp * TU) / kDWarps;
+  R.u1 = ((warp + 1) * TU) / kDWarps;
+  return R;
+}
+
+// stage-wide qweight row -> (part, part-local qweight row)
+__device__ __forceinline__ void dec_locate(const DecStage* S, int vq, int& pi, int& lq) {
+  if (S->epilogue == QEFT_EPI_SWIGLU) { pi = vq & 1; lq = vq >> 1; return; }
+  pi = 0;
+#pragma unroll
+  for (int i = 1; i < QEFT_GEMV_MAX_PARTS; ++i)
+    if (i < S->nparts && vq >= S->part[i].q_begin) pi = i;
+  lq = vq - S->part[pi].q_begin;
+}
+
+// copies with the PTX "ignore-src" predicate: when ign != 0 nothing is read and the destination is zero-filled
+__device__ __forceinline__ void d_cp16z(uint32_t dst, const void* src, int ign) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+               ::"r"(dst), "l"(src), "r"(ign) : "memory");
+}
+// the same for 8 bytes, issued only by lanes with act != 0
+__device__ __forceinline__ void d_cp8z_if(uint32_t dst, const void* src, int act, int ign) {
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %3, 0;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q cp.async.ca.shared.global [%0], [%1], 8, p;\n\t}"
+               ::"r"(dst), "l"(src), "r"(act), "r"(ign) : "memory");
+}
+
+// D: ring depth (units per warp).  M: batch rows (1 or 2); the B fragment's 8 columns are M x 4 digit columns.
+template <int D, int M>
+__global__ void __launch_bounds__(kDThreads, 1)
+decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, unsigned* sync, const DecLayout L) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  constexpr int NCOLS = 4 * M;
+  constexpr uint32_t XSTEP = 128u * NCOLS;                   // digit bytes per 128-column step: [2 halves][NCOLS][4 t][16 B]
+  constexpr uint32_t XHALF = 64u * NCOLS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+
+  const uint32_t ring = d_smem_u32(dsm) + (uint32_t)(warp * D * kSlot);
+  const uint32_t ring_end = ring + D * kSlot;
+  const uint32_t xdig = d_smem_u32(dsm + L.xdig);
+  const uint32_t xsum = d_smem_u32(dsm + L.xsum);            // [nsteps][2] fp32 group sums of x
+  const uint32_t xo = d_smem_u32(dsm + L.xo);                // [M][r] fp16 outlier activations
+  float* part = reinterpret_cast<float*>(dsm + L.part);      // [warp][touch][2 kinds][M][16 rows]
+  float* red = reinterpret_cast<float*>(dsm + L.misc);       // [16 warps][4] staging reductions
+  float* coef = red + kDWarps * 4;                           // [8] flush weights of a quad's accumulator columns
+  const int MT = L.max_touch;
+
+  // the barrier counter only grows; `base` is its value when every CTA of this launch has started
+  const unsigned base = *reinterpret_cast<volatile unsigned*>(sync + 1);
+
+  // ---- prefetch cursor: walks the units of this warp through ALL stages of the launch --------------------------
+  // A tile's units are issued in phases of identical copies (running pointers, one counter); `ld_event` sets up the
+  // next phase: the tile's outlier columns, the next tile, the next stage, or the idle state after the last stage.
+  int ls = s_begin - 1, lj = 0, lvn = 0, lrem = 0, lcnt = 0, lU = 1, lns = 0;
+  const uint8_t* pcur = reinterpret_cast<const uint8_t*>(stages);   // this lane's 16 bytes of row 2g of the unit (any valid address when idle)
+  const uint8_t* scur = pcur;        // lanes 0..7: 8 bytes of scales (lanes 0..3) / scaled zeros (4..7) of qweight row lane & 3
+  uint32_t poff2 = 0, pstride = 0, sinc = 0;   // row 2g+1 - row 2g; bytes per unit; bytes per scale group
+  int wign = 1, sign = 1, sact = 0;  // ignore-src (zero-fill) flags of rows not owned; lanes that copy scales
+  auto ld_phase = [&](int v) {
+    const DecStage* S = stages + ls;
+    const DecRun R = dec_run(S, cta, ncta, warp);
+    const int r = S->r;
+    const int qi = 4 * lj + (g >> 1);
+    const bool own = qi < R.nq;
+    int pi, lq;
+    dec_locate(S, R.qa + (own ? qi : 0), pi, lq);
+    const DecPart& P = S->part[pi];
+    wign = own ? 0 : 1;
+    int n;
+    if (v < lns) {
+      pcur = P.qw + (size_t)lq * (size_t)(2 * S->K) + (size_t)((t >> 1) * 128 + (g & 1) * 64 + (t & 1) * 16) + (size_t)v * 256;
+      poff2 = 32; pstride = 256;
+      n = lns - v;
+      sact = lane < 8;
+      const int qs = 4 * lj + (lane & 3);
+      const bool owns = qs < R.nq;
+      int pis, lqs;
+      dec_locate(S, R.qa + (owns ? qs : 0), pis, lqs);
+      const DecPart& Ps = S->part[pis];
+      const __half* sb = (((lane >> 2) & 1) ? Ps.szeros : Ps.scales) + 4 * lqs;
+      sign = owns ? 0 : 1;
+      const int g128 = S->g128;
+      const bool partial = (S->nchunks & 3) != 0;            // the last step has dead 32-column chunks
+      int grp;
+      if (g128 > 1) { n = 1; grp = v / g128; sinc = 0; }     // uncommon group sizes: one unit per phase
+      else {
+        grp = g128 == 1 ? v : 0;
+        sinc = g128 == 1 ? (uint32_t)(2 * Ps.N) : 0u;
+        if (partial && n > 1) n -= 1;                        // the last step is a phase of its own
+      }
+      if (partial && v == lns - 1 && 4 * v + t >= S->nchunks) wign = 1;
+      scur = reinterpret_cast<const uint8_t*>(sb + (size_t)grp * (size_t)Ps.N);
+    } else {
+      pcur = reinterpret_cast<const uint8_t*>(P.ow + ((size_t)(4 * lq + 2 * (g & 1)) * (size_t)r + (size_t)(8 * t + 32 * (v - lns))));
+      poff2 = (uint32_t)(2 * r); pstride = 64;
+      n = lU - v;
+      sact = 0; sinc = 0;
+    }
+    n = n < lrem ? n : lrem;
+    lcnt = n; lrem -= n; lvn = v + n;
+  };
+  auto ld_next_stage = [&]() {
+    for (;;) {
+      ++ls;
+      if (ls >= s_end) { lcnt = 0x7fffffff; wign = 1; sact = 0; pstride = 0; sinc = 0; poff2 = 0; return; }   // idle: zero-fills
+      const DecStage* S = stages + ls;
+      const DecRun R = dec_run(S, cta, ncta, warp);
+      if (R.u0 < R.u1) {
+        lU = R.U; lns = R.ns; lrem = R.u1 - R.u0;
+        lj = R.u0 / lU;
+        ld_phase(R.u0 - lj * lU);
+        return;
+      }
+    }
+  };
+  auto ld_issue = [&](uint32_t slot) {
+    const uint32_t mine = slot + lane * 16;
+    d_cp16z(mine, pcur, wign);
+    d_cp16z(mine + 512, pcur + poff2, wign);
+    d_cp8z_if(slot + kSlotScale + lane * 8, scur, sact, sign);
+    d_commit();                      // always one group per unit: the group count is the ring's clock
+    pcur += pstride; scur += sinc;
+    if (--lcnt == 0) {
+      if (lrem == 0) ld_next_stage();
+      else if (lvn == lU) { ++lj; ld_phase(0); }
+      else ld_phase(lvn);
+    }
+  };
+
+  ld_next_stage();
+#pragma unroll 1
+  for (int d = 0; d < D - 1; ++d) ld_issue(ring + d * kSlot);
+
+  uint32_t slot = ring, prev_slot = ring + (D - 1) * kSlot;
+  const uint32_t xdig_lane = xdig + (uint32_t)(g * 64 + t * 16);
+  const int has_col = g < NCOLS;
+  // batch 1: lane t = 2 of every quad accumulates the zero-point term (its accumulator columns are no digits)
+  const bool zlane = M == 1 && t == 2;
+  const uint32_t soff_lane = (uint32_t)(kSlotScale + 4 * g + (zlane ? 32 : 0));
+  const int gx = g < M ? g : 0;
+
+  // one unit: wait for the oldest group, refill the slot read one unit ago, fetch this lane's 32 bytes
+#define QEFT_DEC_UNIT_BEGIN()                                   \
+  d_wait<D - 2>();                                              \
+  __syncwarp();                                                 \
+  ld_issue(prev_slot);                                          \
+  const uint32_t mine = slot + lane * 16;                       \
+  const uint4 va = d_lds128(mine), vb = d_lds128(mine + 512);
+#define QEFT_DEC_UNIT_END()                                     \
+  prev_slot = slot;                                             \
+  slot += kSlot;                                                \
+  if (slot == ring_end) slot = ring;
+
+#pragma unroll 1
+  for (int s = s_begin; s < s_end; ++s) {
+    const DecStage* S = stages + s;
+    const DecRun R = dec_run(S, cta, ncta, warp);
+    const int K = S->K, r = S->r, ns = S->nsteps;
+
+    if (s > s_begin) {
+      // ---- stage boundary: every CTA has stored its rows of the previous stage -------------------------------
+      if (tid == 0) {
+        const unsigned want = base + (unsigned)(s - s_begin) * (unsigned)ncta;
+        unsigned got;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(sync) : "memory");
+        } while ((int)(got - want) < 0);
+        if (cta == 0 && s == s_begin + 1)       // every CTA has read `base`: publish the next launch's base
+          *reinterpret_cast<volatile unsigned*>(sync + 1) = base + (unsigned)(s_end - s_begin - 1) * (unsigned)ncta;
+      }
+      __syncthreads();
+    }
+
+    dec_stamp(L, s, 0);
+    // ---- x: four signed-byte digits of a 30-bit fixed point, one exponent per batch row ----------------------
+    {
+      const __half* xg = S->x;
+      const int32_t* gat = S->gather;
+      const __half* nw = S->norm_w;
+      const int live_k = S->nchunks * 32;
+      const int nitems = M * ns * 8;
+      constexpr int kKeep = 3;
+      uint4 keep[kKeep][2];
+      float mx0 = 0.f, mx1 = 0.f, ss0 = 0.f, ss1 = 0.f;
+      // item = (batch row b, step, chunk tt, hs): the 16 columns k0 .. k0+7 and k0+16 .. k0+23, k0 = 128 step + 32 tt + 8 hs
+      auto load_item = [&](int it, uint4& v0, uint4& v1, int& b, bool& live) {
+        const int sb = it >> 3;
+        b = sb / ns;
+        const int st = sb - b * ns;
+        const int k0 = st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8;
+        live = it < nitems && k0 < live_k;
+        v0 = v1 = make_uint4(0u, 0u, 0u, 0u);
+        if (live) {
+          const __half* xr = xg + (size_t)b * K;
+          if (gat) {
+            const int4 i0 = __ldg(reinterpret_cast<const int4*>(gat + k0)), i1 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 4));
+            const int4 i2 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 16)), i3 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 20));
+            auto pk = [&](int a, int c) { return (uint32_t)d_ldcg16(xr + a) | ((uint32_t)d_ldcg16(xr + c) << 16); };
+            v0 = make_uint4(pk(i0.x, i0.y), pk(i0.z, i0.w), pk(i1.x, i1.y), pk(i1.z, i1.w));
+            v1 = make_uint4(pk(i2.x, i2.y), pk(i2.z, i2.w), pk(i3.x, i3.y), pk(i3.z, i3.w));
+          } else {
+            v0 = d_ldcg128(xr + k0);
+            v1 = d_ldcg128(xr + k0 + 16);
+          }
+          if (nw) {
+            // RMSNorm on the way in (HF LlamaRMSNorm: weight * (x * rsqrt(mean x^2 + eps)).to(fp16)): here only the
+            // sum of squares; the scaling happens in pass B
+            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+            if (b == 0) ss0 += ss; else ss1 += ss;
+          }
+        }
+      };
+      auto absmax_item = [&](const uint4& v0, const uint4& v1) {
+        __half2 a = __habs2(*reinterpret_cast<const __half2*>(&v0.x));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v0.y)));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v0.z)));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v0.w)));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.x)));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.y)));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.z)));
+        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.w)));
+        return fmaxf(__low2float(a), __high2float(a));
+      };
+      // x * norm weight (fp32 product of the fp16 inputs), used for the bound of |normalised x|
+      auto scaled_absmax_item = [&](const uint4& v0, const uint4& v1, int it) {
+        const int sb = it >> 3, b = sb / ns, st = sb - b * ns;
+        const int k0 = st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8;
+        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float mxv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + (j < 4 ? 2 * j : 16 + 2 * (j - 4));
+          const int c0 = gat ? gat[k] : k, c1 = gat ? gat[k + 1] : k + 1;
+          const float2 f = half2_bits_to_float2(w[j]);
+          mxv = fmaxf(mxv, fmaxf(fabsf(f.x * __half2float(nw[c0])), fabsf(f.y * __half2float(nw[c1]))));
+        }
+        return mxv;
+      };
+      const int npass = (nitems + kDThreads - 1) / kDThreads;
+      // pass A: all loads of the thread's first kKeep items are in flight together (one L2 round trip)
+#pragma unroll
+      for (int q = 0; q < kKeep; ++q) {
+        int b; bool live;
+        load_item(q * kDThreads + tid, keep[q][0], keep[q][1], b, live);
+        if (q < npass && live) {
+          const float v = nw ? scaled_absmax_item(keep[q][0], keep[q][1], q * kDThreads + tid) : absmax_item(keep[q][0], keep[q][1]);
+          if (b == 0) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+        }
+      }
+      for (int q = kKeep; q < npass; ++q) {
+        uint4 v0, v1; int b; bool live;
+        load_item(q * kDThreads + tid, v0, v1, b, live);
+        if (live) {
+          const float v = nw ? scaled_absmax_item(v0, v1, q * kDThreads + tid) : absmax_item(v0, v1);
+          if (b == 0) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+        }
+      }
+      // the outlier activations (fp16 path): loaded here, stored after the reduction
+      const int nxo = M * (r >> 3);
+      uint4 xo_v = make_uint4(0u, 0u, 0u, 0u);
+      const int xo_tid = kDThreads - 1 - tid;              // the threads the digit items use least
+      if (xo_tid < nxo) {
+        const int b = xo_tid / (r >> 3), jj = xo_tid - b * (r >> 3);
+        const __half* xr = xg + (size_t)b * K;
+        if (gat) {
+          const int4 a = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj)), c = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj + 4));
+          auto pk = [&](int i0, int i1) { return (uint32_t)d_ldcg16(xr + i0) | ((uint32_t)d_ldcg16(xr + i1) << 16); };
+          xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
+        } else {
+          xo_v = d_ldcg128(xr + K - r + 8 * jj);
+        }
+        if (nw) {
+          const uint32_t w[4] = {xo_v.x, xo_v.y, xo_v.z, xo_v.w};
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+          if (b == 0) ss0 += ss; else ss1 += ss;
+        }
+      }
+      // CTA-wide maximum (and sum of squares) per batch row
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+      }
+      if (nw) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+          ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+        }
+      }
+      if (lane == 0) { red[warp * 4 + 0] = mx0; red[warp * 4 + 1] = mx1; red[warp * 4 + 2] = ss0; red[warp * 4 + 3] = ss1; }
+      __syncthreads();
+      mx0 = mx1 = ss0 = ss1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kDWarps; ++w) {
+        mx0 = fmaxf(mx0, red[w * 4 + 0]); mx1 = fmaxf(mx1, red[w * 4 + 1]);
+        ss0 += red[w * 4 + 2]; ss1 += red[w * 4 + 3];
+      }
+      float rs0 = 1.f, rs1 = 1.f;
+      if (nw) {
+        rs0 = rsqrtf(ss0 / (float)K + S->norm_eps);
+        rs1 = rsqrtf(ss1 / (float)K + S->norm_eps);
+        // |w * fp16(x * rs)| <= |w x| rs (1 + 2^-10), rounded once more to fp16: bound with a margin
+        mx0 *= rs0 * 1.002f; mx1 *= rs1 * 1.002f;
+      }
+      // 2^e > max|x|;  X = rint(x 2^(29-e)), |X| < 2^29;  digit d weighs 2^(e-29+8d), and 1/16 for the nibble trick
+      const int e0 = mx0 > 0.f ? (int)((__float_as_uint(mx0) >> 23) & 0xff) - 126 : -100;
+      const int e1 = mx1 > 0.f ? (int)((__float_as_uint(mx1) >> 23) & 0xff) - 126 : -100;
+      const float sc0 = e0 > -100 ? __uint_as_float((uint32_t)(127 + 29 - e0) << 23) : 0.f;
+      const float sc1 = e1 > -100 ? __uint_as_float((uint32_t)(127 + 29 - e1) << 23) : 0.f;
+      if (tid < 8) {
+        // coef[2t], coef[2t+1]: what lane t of a quad multiplies its two accumulator columns with at a flush
+        const int b = tid >> 2, d = tid & 3;
+        const int e = b ? e1 : e0;
+        float c = (e > -100 && b < M) ? __uint_as_float((uint32_t)(127 + e - 29 + 8 * d - 4) << 23) : 0.f;
+        if (M == 1 && tid == 4) c = 1.f;            // batch 1: lane t = 2 carries the zero-point sums unscaled
+        coef[tid] = c;
+      }
+      // pass B: digits
+      for (int q = 0; q < npass; ++q) {
+        const int it = q * kDThreads + tid;
+        uint4 v0, v1; int b; bool live;
+        if (q < kKeep) {
+          // select the kept pair without dynamic register indexing
+          v0 = keep[0][0]; v1 = keep[0][1];
+#pragma unroll
+          for (int j = 1; j < kKeep; ++j)
+            if (q == j) { v0 = keep[j][0]; v1 = keep[j][1]; }
+          const int sb = it >> 3;
+          b = sb / ns;
+          const int st = sb - b * ns;
+          live = it < nitems && (st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8) < live_k;
+        } else {
+          float sv0 = ss0, sv1 = ss1;                    // (load_item adds to the sums: keep them)
+          load_item(it, v0, v1, b, live);
+          ss0 = sv0; ss1 = sv1;
+        }
+        const bool valid = it < nitems;
+        const int sb = valid ? (it >> 3) : 0;
+        const int st = sb - (sb / ns) * ns;
+        const int tt = (it >> 1) & 3, hs = it & 1;
+        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float2 f[8];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = half2_bits_to_float2(w[j]);
+        if (nw && live) {
+          const int k0 = st * 128 + tt * 32 + hs * 8;
+          const float rs = b ? rs1 : rs0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = k0 + (j < 4 ? 2 * j : 16 + 2 * (j - 4));
+            const int c0 = gat ? gat[k] : k, c1 = gat ? gat[k + 1] : k + 1;
+            // the reference's two roundings: (x * rs).to(fp16), then * weight in fp16
+            const __half h0 = __hmul(nw[c0], __float2half_rn(f[j].x * rs)), h1 = __hmul(nw[c1], __float2half_rn(f[j].y * rs));
+            f[j] = make_float2(__half2float(h0), __half2float(h1));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[j].x + f[j].y;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        if (valid) {
+          const float sc = b ? sc1 : sc0;
+          auto digits = [&](float v) {
+            const int X = __float2int_rn(v * sc);
+            return (uint32_t)(X + 0x00808080) ^ 0x00808080u;       // bytes = signed digits d0..d3
+          };
+          uint32_t dg[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { dg[2 * j] = digits(f[j].x); dg[2 * j + 1] = digits(f[j].y); }
+          // digit row d, word c: bytes {first[2c], second[2c], first[2c+1], second[2c+1]} (first = k0 + ., second = k0 + 16 + .)
+          const uint32_t dst = xdig + (uint32_t)(st * XSTEP + hs * XHALF + (4 * b) * 64 + tt * 16);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const uint32_t sel = 0x0040u + 0x11u * (uint32_t)d;
+            uint32_t ww[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              ww[c] = d_prmt(d_prmt(dg[2 * c], dg[8 + 2 * c], sel), d_prmt(dg[2 * c + 1], dg[8 + 2 * c + 1], sel), 0x5410u);
+            d_sts128(dst + d * 64, ww[0], ww[1], ww[2], ww[3]);
+          }
+          if ((it & 7) == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + (uint32_t)(st * 8 + b * 4)), "f"(sum) : "memory");
+        }
+      }
+      if (xo_tid < nxo) {
+        const int b = xo_tid / (r >> 3), jj = xo_tid - b * (r >> 3);
+        if (nw) {
+          const float rs = b ? rs1 : rs0;
+          uint32_t w[4] = {xo_v.x, xo_v.y, xo_v.z, xo_v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = K - r + 8 * jj + 2 * j;
+            const int c0 = gat ? gat[k] : k, c1 = gat ? gat[k + 1] : k + 1;
+            const float2 f = half2_bits_to_float2(w[j]);
+            const __half2 h = __halves2half2(__hmul(nw[c0], __float2half_rn(f.x * rs)), __hmul(nw[c1], __float2half_rn(f.y * rs)));
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          xo_v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        d_sts128(xo + (uint32_t)((b * r + 8 * jj) * 2), xo_v.x, xo_v.y, xo_v.z, xo_v.w);
+      }
+      __syncthreads();
+    }
+
+    dec_stamp(L, s, 1);
+    // ---- this warp's units of the stage ------------------------------------------------------------------------
+    {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};    // rows 2g, 2g+1 x accumulator columns 2t, 2t+1: sum over groups of scale * P
+      float zacc0 = 0.f, zacc1 = 0.f;         // M = 2: rows 2g, 2g+1, sum over groups of scaled zero * X_g, batch row t >> 1
+      float yo[4] = {0.f, 0.f, 0.f, 0.f};     // outlier columns: rows 2g, 2g+1 x batch rows 2t, 2t+1
+      uint4 xe = make_uint4(0u, 0u, 0u, 0u), xq = xe;
+      const int U = R.U;
+      int v = R.u0 - (R.u0 / U) * U, rem = R.u1 - R.u0, touch = 0;
+      while (rem > 0) {
+        if (v < ns) {
+          int n = ns - v < rem ? ns - v : rem;
+          uint32_t xc = xdig_lane + (uint32_t)v * XSTEP;
+          uint32_t xsa = xsum + (uint32_t)(v * 8 + (M == 2 ? (t >> 1) * 4 : 0));
+          rem -= n; v += n;
+#pragma unroll 1
+          for (; n > 0; --n) {
+            // one 128-column int4 step of 16 rows: two AND masks per word (low nibbles q, high nibbles 16 q: both valid
+            // u8), 4 IMMA with exact s32 accumulation; 16 lo + hi = 16 sum(q X)
+            QEFT_DEC_UNIT_BEGIN();
+            d_lds128_if(xe, xc, has_col);
+            d_lds128_if(xq, xc + XHALF, has_col);
+            const uint32_t sw = d_lds32(slot + soff_lane);
+            const float xs = d_ldsf(xsa);
+            constexpr uint32_t kLoM = 0x0f0f0f0fu, kHiM = 0xf0f0f0f0u;
+            int lo[4], hi[4];
+            d_imma0(lo, va.x & kLoM, vb.x & kLoM, va.y & kLoM, vb.y & kLoM, xe.x, xe.y);
+            d_imma0(hi, va.x & kHiM, vb.x & kHiM, va.y & kHiM, vb.y & kHiM, xq.x, xq.y);
+            d_imma(lo, va.z & kLoM, vb.z & kLoM, va.w & kLoM, vb.w & kLoM, xe.z, xe.w);
+            d_imma(hi, va.z & kHiM, vb.z & kHiM, va.w & kHiM, vb.w & kHiM, xq.z, xq.w);
+            const float2 sc = half2_bits_to_float2(sw);
+            float f0 = (float)(lo[0] * 16 + hi[0]), f2 = (float)(lo[2] * 16 + hi[2]);
+            const float f1 = (float)(lo[1] * 16 + hi[1]), f3 = (float)(lo[3] * 16 + hi[3]);
+            if (M == 1) {
+              if (zlane) { f0 = xs; f2 = xs; }               // scaled zero x group sum of x in the zero-point lane
+            } else {
+              const float2 zz = half2_bits_to_float2(d_lds32(slot + kSlotScale + 32 + 4 * g));
+              zacc0 = fmaf(zz.x, xs, zacc0);
+              zacc1 = fmaf(zz.y, xs, zacc1);
+            }
+            acc[0] = fmaf(sc.x, f0, acc[0]);
+            acc[1] = fmaf(sc.x, f1, acc[1]);
+            acc[2] = fmaf(sc.y, f2, acc[2]);
+            acc[3] = fmaf(sc.y, f3, acc[3]);
+            xc += XSTEP; xsa += 8;
+            QEFT_DEC_UNIT_END();
+          }
+        }
+        if (rem > 0 && v < U) {
+          int n = U - v < rem ? U - v : rem;
+          uint32_t xoa = xo + (uint32_t)((gx * r + 8 * t + 32 * (v - ns)) * 2);
+          rem -= n; v += n;
+#pragma unroll 1
+          for (; n > 0; --n) {
+            // 32 fp16 outlier columns of 16 rows: 2 HMMA
+            QEFT_DEC_UNIT_BEGIN();
+            const uint4 xv = d_lds128(xoa);
+            mma_m16n8k16_f16f32(yo, va.x, vb.x, va.y, vb.y, xv.x, xv.y);
+            mma_m16n8k16_f16f32(yo, va.z, vb.z, va.w, vb.w, xv.z, xv.w);
+            xoa += 64;
+            QEFT_DEC_UNIT_END();
+          }
+        }
+        {
+          // end of this warp's share of the tile: accumulator columns -> one value per (row, batch row), to this warp's slice
+          const float c0 = coef[2 * t], c1 = coef[2 * t + 1];
+          float v1 = fmaf(c0, acc[0], c1 * acc[1]), v2 = fmaf(c0, acc[2], c1 * acc[3]);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+          if (M == 1) {
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+          }
+          float* dst = part + ((size_t)(warp * MT + touch) * 2) * (size_t)(M * 16);
+          if (M == 1) {
+            if (t == 0) { dst[2 * g] = v1; dst[2 * g + 1] = v2; }
+          } else if ((t & 1) == 0) {
+            dst[(t >> 1) * 16 + 2 * g] = v1 + zacc0;
+            dst[(t >> 1) * 16 + 2 * g + 1] = v2 + zacc1;
+          }
+          if (t == 0) {
+            float* dso = dst + M * 16;
+            dso[2 * g] = yo[0]; dso[2 * g + 1] = yo[2];
+            if (M > 1) { dso[16 + 2 * g] = yo[1]; dso[16 + 2 * g + 1] = yo[3]; }
+          }
+          acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+          zacc0 = zacc1 = 0.f;
+          yo[0] = yo[1] = yo[2] = yo[3] = 0.f;
+          ++touch;
+          if (v == U) v = 0;
+        }
+      }
+    }
+    __syncthreads();
+    dec_stamp(L, s, 2);
+
+    // ---- add the warps' slices in a fixed order, epilogue, store the rows this CTA owns -------------------------
+    {
+      const int U = R.U, TU = R.ntiles * U;
+      const int epi = S->epilogue;
+      const int nitems = R.ntiles * 16 * M;
+      for (int i = tid; i < nitems; i += kDThreads) {
+        const int b = i % M, rr = (i / M) & 15, j = i / (16 * M);
+        const int qi = 4 * j + (rr >> 2);
+        if (qi >= R.nq) continue;
+        if (epi == QEFT_EPI_SWIGLU && (rr & 4)) continue;          // up rows are consumed by their gate rows
+        auto tile_sum = [&](int row) {
+          float a = 0.f;
+#pragma unroll 1
+          for (int w = 0; w < kDWarps; ++w) {
+            const int w0 = (w * TU) / kDWarps, w1 = ((w + 1) * TU) / kDWarps;
+            if (w0 < w1 && w0 < (j + 1) * U && w1 > j * U) {      // the warp's (non-empty) run overlaps tile j
+              const float* src = part + ((size_t)(w * MT + (j - w0 / U)) * 2) * (size_t)(M * 16);
+              a += src[b * 16 + row] + src[M * 16 + b * 16 + row];
+            }
+          }
+          return a;
+        };
+        int pi, lq;
+        dec_locate(S, R.qa + qi, pi, lq);
+        const DecPart& P = S->part[pi];
+        const int n = 4 * lq + (rr & 3);
+        float a = tile_sum(rr);
+        if (P.bias) a += __half2float(P.bias[n]);
+        __half h = __float2half_rn(a);
+        if (epi == QEFT_EPI_SWIGLU) {
+          // silu(gate) * up, both rounded to fp16 first like the unfused linears (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x))
+          const DecPart& Pu = S->part[1];
+          float u = tile_sum(rr + 4);
+          if (Pu.bias) u += __half2float(Pu.bias[n]);
+          const float gf = __half2float(h);
+          const __half sg = __float2half_rn(gf / (1.f + __expf(-gf)));
+          h = __hmul(sg, __float2half_rn(u));
+        } else if (S->residual) {
+          const __half res = __ushort_as_half(d_ldcg16(S->residual + (size_t)b * P.N + n));
+          h = __hadd(res, h);
+        }
+        P.y[(size_t)b * P.N + n] = h;
+      }
+    }
+    if (s + 1 < s_end) {
+      __syncthreads();
+      if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
+    }
+    dec_stamp(L, s, 3);
+  }
+  d_wait<0>();
+}
+#undef QEFT_DEC_UNIT_BEGIN
+#undef QEFT_DEC_UNIT_END
+
+// ----------------------------------------------------------------------------------------------------
+struct DecProgram {
+  DecStage* d_stages = nullptr;
+  unsigned* d_sync = nullptr;
+  unsigned long long* d_stamps = nullptr;
+  std::vector<DecStage> h_stages;
+  int m = 1;
+  int device = 0;
+  int nsm = 0;
+};
+
+static int dec_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int D, int M>
+static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, size_t smem, int grid, cudaStream_t stream) {
+  auto kern = decode_w4_kernel<D, M>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDSmemMax);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kDThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: they wait for one another at stage boundaries
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (s1 - s0 > 1) ? 1 : 0;
+  const DecStage* st = p->d_stages;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L);
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return QEFT_OK;
+}
+
+}  // namespace qeft
+
+using namespace qeft;
+
+extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int nstages, int m, qeft_decode_program_t** out) {
+  if (!stages || !out) return QEFT_E_NULL;
+  if (nstages < 1) return QEFT_E_SHAPE;
+  if (m < 1 || m > 2) return QEFT_E_BATCH;
+  DecProgram* p = new DecProgram();
+  p->m = m;
+  p->h_stages.resize(nstages);
+  for (int s = 0; s < nstages; ++s) {
+    const qeft_decode_stage_t& q = stages[s];
+    DecStage& d = p->h_stages[s];
+    d = DecStage{};
+    int G = q.G == -1 ? q.K : q.G;
+    const int K = q.K, r = q.r;
+    int st = QEFT_OK;
+    if (!q.x) st = QEFT_E_NULL;
+    else if (q.nparts < 1 || q.nparts > QEFT_GEMV_MAX_PARTS) st = QEFT_E_SHAPE;
+    else if (K <= 0 || K % 64 != 0 || G <= 0 || K % G != 0 || (G % 128 != 0 && G != K)) st = QEFT_E_SHAPE;
+    else if (r < 0 || r % 32 != 0 || r >= K) st = QEFT_E_SHAPE;
+    else if (!check_align16(q.x) || (q.x_gather && !check_align16(q.x_gather))) st = QEFT_E_ALIGN;
+    else if (q.epilogue != QEFT_EPI_NONE && q.epilogue != QEFT_EPI_SWIGLU && q.epilogue != QEFT_EPI_RESIDUAL) st = QEFT_E_DTYPE;
+    else if (q.epilogue == QEFT_EPI_SWIGLU && (q.nparts != 2 || q.parts[0].N != q.parts[1].N)) st = QEFT_E_SHAPE;
+    else if (q.epilogue == QEFT_EPI_RESIDUAL && (q.nparts != 1 || !q.residual)) st = QEFT_E_NULL;
+    int total_q = 0;
+    for (int i = 0; st == QEFT_OK && i < q.nparts; ++i) {
+      const qeft_gemv_part_t& a = q.parts[i];
+      const bool need_y = !(q.epilogue == QEFT_EPI_SWIGLU && i == 1);
+      if (!a.qweight || !a.scales || !a.scaled_zeros || (need_y && !a.y) || (r > 0 && !a.oweight)) st = QEFT_E_NULL;
+      else if (a.N <= 0 || a.N % 8 != 0) st = QEFT_E_SHAPE;
+      else if (!check_align16(a.qweight) || !check_align16(a.scales) || !check_align16(a.scaled_zeros) ||
+               (r > 0 && !check_align16(a.oweight)) || (r % 8 != 0))
+        st = QEFT_E_ALIGN;
+      if (st != QEFT_OK) break;
+      DecPart& dp = d.part[i];
+      dp.qw = static_cast<const uint8_t*>(a.qweight);
+      dp.scales = static_cast<const __half*>(a.scales);
+      dp.szeros = static_cast<const __half*>(a.scaled_zeros);
+      dp.ow = r > 0 ? static_cast<const __half*>(a.oweight) : static_cast<const __half*>(a.scales);
+      dp.bias = static_cast<const __half*>(a.bias);
+      dp.y = static_cast<__half*>(a.y);
+      dp.N = a.N;
+      dp.q_begin = total_q;
+      total_q += a.N / 4;
+    }
+    if (st != QEFT_OK) { delete p; return st; }
+    d.x = static_cast<const __half*>(q.x);
+    d.gather = q.x_gather;
+    d.norm_w = static_cast<const __half*>(q.norm_weight);
+    d.norm_eps = q.norm_eps;
+    d.residual = q.epilogue == QEFT_EPI_RESIDUAL ? static_cast<const __half*>(q.residual) : nullptr;
+    d.nparts = q.nparts;
+    d.K = K; d.r = r;
+    d.g128 = (G == K) ? 0 : G / 128;
+    d.nsteps = cdiv(K - r, 128);
+    d.nchunks = (K - r) / 32;
+    d.nou = r / 32;
+    d.total_q = total_q;
+    d.epilogue = q.epilogue;
+  }
+  cudaGetDevice(&p->device);
+  if (cudaDeviceGetAttribute(&p->nsm, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess || p->nsm <= 0) p->nsm = 148;
+  cudaError_t e = cudaMalloc(&p->d_stages, sizeof(DecStage) * (size_t)nstages);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_sync, 256);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_stages, p->h_stages.data(), sizeof(DecStage) * (size_t)nstages, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(p->d_sync, 0, 256);
+  if (e != cudaSuccess) {
+    if (p->d_stages) cudaFree(p->d_stages);
+    if (p->d_sync) cudaFree(p->d_sync);
+    delete p;
+    return (int)e;
+  }
+  *out = reinterpret_cast<qeft_decode_program_t*>(p);
+  return QEFT_OK;
+}
+
+extern "C" int qeft_decode_program_destroy(qeft_decode_program_t* prog) {
+  if (!prog) return QEFT_E_NULL;
+  DecProgram* p = reinterpret_cast<DecProgram*>(prog);
+  cudaFree(p->d_stages);
+  cudaFree(p->d_sync);
+  if (p->d_stamps) cudaFree(p->d_stamps);
+  delete p;
+  return QEFT_OK;
+}
+
+// debug: host_out[nstages][4 CTAs][4] globaltimer stamps of the last run (QEFT_DECODE_STAMPS=1)
+extern "C" __attribute__((visibility("default"))) int qeft_decode_debug_stamps(qeft_decode_program_t* prog, unsigned long long* host_out) {
+  if (!prog || !host_out) return QEFT_E_NULL;
+  DecProgram* p = reinterpret_cast<DecProgram*>(prog);
+  if (!p->d_stamps) return QEFT_E_UNSUPPORTED;
+  cudaError_t e = cudaMemcpy(host_out, p->d_stamps, p->h_stages.size() * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? QEFT_OK : (int)e;
+}
+
+extern "C" int qeft_decode_program_num_stages(const qeft_decode_program_t* prog) {
+  return prog ? (int)reinterpret_cast<const DecProgram*>(prog)->h_stages.size() : QEFT_E_NULL;
+}
+
+extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_begin, int stage_end, unsigned flags,
+                                       qeft_stream_t stream) {
+  (void)flags;
+  if (!prog) return QEFT_E_NULL;
+  DecProgram* p = reinterpret_cast<DecProgram*>(prog);
+  const int n = (int)p->h_stages.size();
+  if (stage_begin < 0 || stage_end > n || stage_begin >= stage_end) return QEFT_E_SHAPE;
+  static const int grid_env = dec_env_int("QEFT_DECODE_GRID", 0);
+  static const int depth_env = dec_env_int("QEFT_DECODE_DEPTH", 0);
+  const int grid = grid_env > 0 ? grid_env : p->nsm;
+  const int m = p->m;
+  // shared memory: the largest stage of the range sizes the x buffers and the partial-sum slices
+  int max_steps = 0, max_r = 0, max_touch = 1;
+  for (int s = stage_begin; s < stage_end; ++s) {
+    const DecStage& d = p->h_stages[s];
+    max_steps = d.nsteps > max_steps ? d.nsteps : max_steps;
+    max_r = d.r > max_r ? d.r : max_r;
+    const int al = d.epilogue == QEFT_EPI_SWIGLU ? 2 : 1;
+    const int nq_max = al * cdiv(d.total_q / al, grid);
+    const int T = cdiv(nq_max, 4), U = d.nsteps + d.nou;
+    const int run = cdiv(T * U, kDWarps);
+    const int touch = (run + U - 2) / U + 1;     // a run of `run` units starting anywhere in a tile
+    max_touch = touch > max_touch ? touch : max_touch;
+  }
+  DecLayout L;
+  size_t off = 0;   // the ring comes first; its size is decided below
+  const size_t xdig = (size_t)max_steps * 128 * 4 * m;
+  const size_t xsum = (size_t)max_steps * 8 + 16;
+  const size_t xo = (size_t)m * max_r * 2 + 16;
+  const size_t part = (size_t)kDWarps * max_touch * 2 * m * 16 * sizeof(float);
+  const size_t misc = 1024;
+  const size_t fixed = ((xdig + 127) & ~(size_t)127) + ((xsum + 127) & ~(size_t)127) + ((xo + 127) & ~(size_t)127) +
+                       ((part + 127) & ~(size_t)127) + misc;
+  if (fixed + (size_t)kDWarps * 3 * kSlot > kDSmemMax) return QEFT_E_UNSUPPORTED;
+  int depth = (int)((kDSmemMax - fixed) / ((size_t)kDWarps * kSlot));
+  if (depth_env > 0 && depth > depth_env) depth = depth_env;
+  depth = depth >= 10 ? 10 : (depth >= 8 ? 8 : (depth >= 6 ? 6 : (depth >= 4 ? 4 : 3)));
+  off = (size_t)kDWarps * depth * kSlot;
+  off = (off + 127) & ~(size_t)127;
+  L.xdig = (int)off; off += (xdig + 127) & ~(size_t)127;
+  L.xsum = (int)off; off += (xsum + 127) & ~(size_t)127;
+  L.xo = (int)off; off += (xo + 127) & ~(size_t)127;
+  L.part = (int)off; off += (part + 127) & ~(size_t)127;
+  L.misc = (int)off; off += misc;
+  L.max_touch = max_touch;
+  static const int stamps_env = dec_env_int("QEFT_DECODE_STAMPS", 0);
+  if (stamps_env && !p->d_stamps) {
+    const size_t bytes = (size_t)n * 16 * sizeof(unsigned long long);
+    if (cudaMalloc(&p->d_stamps, bytes) == cudaSuccess) cudaMemset(p->d_stamps, 0, bytes);
+    else p->d_stamps = nullptr;
+  }
+  L.stamps = p->d_stamps;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define QEFT_DEC_LAUNCH(DD) \
+  (m == 1 ? dec_launch<DD, 1>(p, stage_begin, stage_end, L, off, grid, st) : dec_launch<DD, 2>(p, stage_begin, stage_end, L, off, grid, st))
+  switch (depth) {
+    case 10: return QEFT_DEC_LAUNCH(10);
+    case 8: return QEFT_DEC_LAUNCH(8);
+    case 6: return QEFT_DEC_LAUNCH(6);
+    case 4: return QEFT_DEC_LAUNCH(4);
+    default: return QEFT_DEC_LAUNCH(3);
+  }
+#undef QEFT_DEC_LAUNCH
+}

@@ -124,6 +124,31 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+
+// Activation loads.  When x is the gathered buffer of an earlier launch of a column-sharded chain (wait_flag set), peers
+// may still be storing into it while this kernel is already resident (programmatic dependent launch): the read-only
+// (.nc) path requires data that is constant for the kernel's lifetime, so those launches read x through L2 (.cg) after
+// the acquire of the arrival counter.  Everything else keeps the read-only path.
+__device__ __forceinline__ uint4 ldx_v4(const void* p, bool coherent) {
+  uint4 r;
+  if (coherent) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  else r = ldg_nc_v4(p);
+  return r;
+}
+__device__ __forceinline__ uint2 ldx_v2(const void* p, bool coherent) {
+  uint2 r;
+  if (coherent) asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  else r = ldg_nc_v2(p);
+  return r;
+}
+__device__ __forceinline__ unsigned short ldx_u16(const void* p, bool coherent) {
+  unsigned short r;
+  if (coherent) asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+  else r = ldg_nc_u16(p);
+  return r;
+}
+__device__ __forceinline__ __half ldx_h(const __half* p, bool coherent) { return __ushort_as_half(ldx_u16(p, coherent)); }
+
 __device__ __forceinline__ void stamp(const GemvParams& p, int i) {
   if (p.stamps && threadIdx.x == 0) {
     unsigned long long t;
@@ -179,6 +204,7 @@ gemv_w4_kernel(const GemvParams p) {
   const int g = lane >> 2, t = lane & 3;
   const int ra = 8 * (g >> 2) + (g & 3), rb = ra + 4;   // tile rows of this lane's two accumulator rows
   const int K = p.K, r = p.r, m = p.m;
+  const bool xcoh = p.wait_flag != nullptr;     // x is a gathered buffer written during this chain: coherent loads
   const int nsteps = p.nsteps, nchunks = p.nchunks;
   const int nku = p.nku, upt = p.nku + p.nou;
   const bool inter = p.ow_layout == QEFT_OW_INTERLEAVED;
@@ -372,8 +398,8 @@ gemv_w4_kernel(const GemvParams p) {
           const int sb = it >> 3, b = sb / nsteps, s = sb - b * nsteps;
           const int k0 = s * 128 + ((it >> 1) & 3) * 32 + 8 * (it & 1);
           if (k0 < live_k) {
-            pre[q][0] = ldg_nc_v4(xg + (size_t)b * K + k0);
-            pre[q][1] = ldg_nc_v4(xg + (size_t)b * K + k0 + 16);
+            pre[q][0] = ldx_v4(xg + (size_t)b * K + k0, xcoh);
+            pre[q][1] = ldx_v4(xg + (size_t)b * K + k0 + 16, xcoh);
           }
         }
       }
@@ -400,7 +426,7 @@ gemv_w4_kernel(const GemvParams p) {
         pre[q][0] = pre[q][1] = make_uint4(0u, 0u, 0u, 0u);
         if (glive[q]) {
           const unsigned short* xr = grow[q];
-          auto pk = [&](int a, int b2) { return (uint32_t)xr[a] | ((uint32_t)xr[b2] << 16); };
+          auto pk = [&](int a, int b2) { return (uint32_t)ldx_u16(xr + a, xcoh) | ((uint32_t)ldx_u16(xr + b2, xcoh) << 16); };
           pre[q][0] = make_uint4(pk(gi[q][0].x, gi[q][0].y), pk(gi[q][0].z, gi[q][0].w), pk(gi[q][1].x, gi[q][1].y), pk(gi[q][1].z, gi[q][1].w));
           pre[q][1] = make_uint4(pk(gi[q][2].x, gi[q][2].y), pk(gi[q][2].z, gi[q][2].w), pk(gi[q][3].x, gi[q][3].y), pk(gi[q][3].z, gi[q][3].w));
         }
@@ -419,10 +445,10 @@ gemv_w4_kernel(const GemvParams p) {
         const int4* ip = reinterpret_cast<const int4*>(p.gather + K - r + 8 * jj);
         const int4 a = __ldg(ip), c = __ldg(ip + 1);
         const unsigned short* xr = reinterpret_cast<const unsigned short*>(xrow);
-        auto pk = [&](int i0, int i1) { return (uint32_t)xr[i0] | ((uint32_t)xr[i1] << 16); };
+        auto pk = [&](int i0, int i1) { return (uint32_t)ldx_u16(xr + i0, xcoh) | ((uint32_t)ldx_u16(xr + i1, xcoh) << 16); };
         xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
       } else {
-        xo_v = ldg_nc_v4(xrow + K - r + 8 * jj);
+        xo_v = ldx_v4(xrow + K - r + 8 * jj, xcoh);
       }
     }
 #pragma unroll 1
@@ -449,11 +475,11 @@ gemv_w4_kernel(const GemvParams p) {
         } else if (p.gather) {
           __half tmp[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { tmp[j] = xrow[p.gather[k0 + j]]; tmp[8 + j] = xrow[p.gather[k0 + 16 + j]]; }
+          for (int j = 0; j < 8; ++j) { tmp[j] = ldx_h(xrow + p.gather[k0 + j], xcoh); tmp[8 + j] = ldx_h(xrow + p.gather[k0 + 16 + j], xcoh); }
 #pragma unroll
           for (int j = 0; j < 8; ++j) w[j] = reinterpret_cast<uint32_t*>(tmp)[j];
         } else {
-          const uint4 v0 = ldg_nc_v4(xrow + k0), v1 = ldg_nc_v4(xrow + k0 + 16);
+          const uint4 v0 = ldx_v4(xrow + k0, xcoh), v1 = ldx_v4(xrow + k0 + 16, xcoh);
           w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
         }
       }
@@ -526,10 +552,10 @@ gemv_w4_kernel(const GemvParams p) {
         if (p.gather) {
           __half tmp[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) tmp[e] = xrow[p.gather[K - r + 8 * jj + e]];
+          for (int e = 0; e < 8; ++e) tmp[e] = ldx_h(xrow + p.gather[K - r + 8 * jj + e], xcoh);
           v = *reinterpret_cast<uint4*>(tmp);
         } else {
-          v = ldg_nc_v4(xrow + K - r + 8 * jj);
+          v = ldx_v4(xrow + K - r + 8 * jj, xcoh);
         }
         *reinterpret_cast<uint4*>(xo + (size_t)b * r + 8 * jj) = v;
       }
@@ -551,12 +577,12 @@ gemv_w4_kernel(const GemvParams p) {
             if (XS && p.gather) {
               __half tmp[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) tmp[j] = xrow[p.gather[k + j]];
+              for (int j = 0; j < 16; ++j) tmp[j] = ldx_h(xrow + p.gather[k + j], xcoh);
               v0 = *reinterpret_cast<uint4*>(tmp);
               v1 = *reinterpret_cast<uint4*>(tmp + 8);
             } else {
-              v0 = ldg_nc_v4(xrow + k);
-              v1 = ldg_nc_v4(xrow + k + 8);
+              v0 = ldx_v4(xrow + k, xcoh);
+              v1 = ldx_v4(xrow + k + 8, xcoh);
             }
             const float2 a0 = half2_bits_to_float2(v0.x), a1 = half2_bits_to_float2(v0.y);
             const float2 a2 = half2_bits_to_float2(v0.z), a3 = half2_bits_to_float2(v0.w);
@@ -590,10 +616,10 @@ gemv_w4_kernel(const GemvParams p) {
           if (p.gather) {
             __half tmp[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) tmp[e] = xrow[p.gather[K - r + 8 * j + e]];
+            for (int e = 0; e < 8; ++e) tmp[e] = ldx_h(xrow + p.gather[K - r + 8 * j + e], xcoh);
             v = *reinterpret_cast<uint4*>(tmp);
           } else {
-            v = ldg_nc_v4(xrow + K - r + 8 * j);
+            v = ldx_v4(xrow + K - r + 8 * j, xcoh);
           }
           *reinterpret_cast<uint4*>(xo + (size_t)b * r + 8 * j) = v;
         }
@@ -633,7 +659,7 @@ gemv_w4_kernel(const GemvParams p) {
       const __half* xp = xg_lane + s * 128 + t * 32;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 v = live ? ldg_nc_v4(xp + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 v = live ? ldx_v4(xp + 8 * j, xcoh) : make_uint4(0u, 0u, 0u, 0u);
         xb[4 * j + 0] = v.x; xb[4 * j + 1] = v.y; xb[4 * j + 2] = v.z; xb[4 * j + 3] = v.w;
       }
     }
@@ -763,7 +789,7 @@ gemv_w4_kernel(const GemvParams p) {
             const uint4 u4 = wv[j];               // {ra, rb} at columns c0 + 16 j + 4t .. + 3
             uint2 xv;
             if (XS) xv = lds_v2(xo_lane + (uint32_t)((c0 + 16 * j + 4 * t) * 2));
-            else xv = ldg_nc_v2(xg_lane + K - r + c0 + 16 * j + 4 * t);
+            else xv = ldx_v2(xg_lane + K - r + c0 + 16 * j + 4 * t, xcoh);
             mma_m16n8k16_f16f32(I8 ? yo : ya, prmt(u4.x, u4.y, 0x5410), prmt(u4.x, u4.y, 0x7632), prmt(u4.z, u4.w, 0x5410),
                                 prmt(u4.z, u4.w, 0x7632), xv.x, xv.y);
           }
@@ -775,7 +801,7 @@ gemv_w4_kernel(const GemvParams p) {
             const uint4 ua = si ? w2 : w0, ub = si ? w3 : w1;   // rows ra / rb, columns c0 + 32 si + 8t .. + 7
             uint4 xv;
             if (XS) xv = lds_v4(xo_lane + (uint32_t)((c0 + 32 * si + 8 * t) * 2));
-            else xv = ldg_nc_v4(xg_lane + K - r + c0 + 32 * si + 8 * t);
+            else xv = ldx_v4(xg_lane + K - r + c0 + 32 * si + 8 * t, xcoh);
             mma_m16n8k16_f16f32(I8 ? yo : ya, ua.x, ub.x, ua.y, ub.y, xv.x, xv.y);
             mma_m16n8k16_f16f32(I8 ? yo : ya, ua.z, ub.z, ua.w, ub.w, xv.z, xv.w);
           }
@@ -839,6 +865,18 @@ gemv_w4_kernel(const GemvParams p) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     atomicMax(p.stamps + 6, t);
+  }
+}
+
+// Consumer side of the arrival-counter protocol for code that is not one of the chain's kernels (a copy to the host,
+// any other stream work): returns once every rank's slice of the launch has landed in this rank's gathered buffer.
+__global__ void gather_wait_kernel(const uint32_t* flag, const uint32_t* epoch, int nranks) {
+  if (threadIdx.x == 0) {
+    const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(epoch) * (uint32_t)nranks * kArrivalsPerLaunch;
+    uint32_t got;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(flag) : "memory");
+    } while ((int)(got - want) < 0);
   }
 }
 
@@ -1047,6 +1085,16 @@ extern "C" int qeft_gemv_w4_multi_gather(const void* x, const qeft_gemv_part_t* 
                                          const qeft_gather_t* gather, qeft_stream_t stream) {
   if (!gather) return QEFT_E_NULL;
   return gemv_entry(x, parts, nparts, ow_layout, x_gather, m, K, r, G, flags, gather, stream);
+}
+
+extern "C" int qeft_gather_wait(const uint32_t* arrival_counter, const uint32_t* epoch, int nranks, qeft_stream_t stream) {
+  if (!arrival_counter || !epoch) return QEFT_E_NULL;
+  if (nranks < 1 || nranks > QEFT_MAX_RANKS) return QEFT_E_SHAPE;
+  gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(arrival_counter, epoch, nranks);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  count_launch();
+  return QEFT_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int qeft_gemv_debug_stamps(unsigned long long* host_out, int nslots) {

@@ -75,6 +75,26 @@ class PackedDecoderStack:
             self.grp_local.append(gl)
         self.pg = None
         self.graph = None
+        self.program = None
+
+    def enable_program(self):
+        """The whole token as ONE launch of the persistent decode kernel (``qeft_cuda.DecodeProgram``): 4 stages per
+        block, stage boundaries are gpu-scope barriers inside the kernel.  Same inputs, outputs and arithmetic
+        bytes as :meth:`step_eager`; unsharded stacks only."""
+        assert self.world == 1 and self.fused
+        stages = []
+        for blk, out in zip(self.blocks, self.out):
+            for names in self.groups:
+                x = self.x_f if names[0] == "down" else self.x_h
+                st = {"x": x, "K": x.shape[-1], "r": self.r, "G": self.G,
+                      "parts": [{"qweight": blk[n]["qweight"], "scales": blk[n]["scales"],
+                                 "scaled_zeros": blk[n]["scaled_zeros"], "oweight": blk[n].get("oweight"),
+                                 "bias": blk[n].get("bias"), "N": blk[n]["N"], "y": out[n]} for n in names]}
+                if names[0] == "o" and self.r > 0:
+                    st["x_gather"] = blk["o"]["reorder_ids32"]
+                stages.append(st)
+        self.program = qeft_cuda.DecodeProgram(stages, m=self.batch)
+        return self.program
 
     def enable_allgather(self, process_group):
         """Column-sharded execution: after each launch group, all-gather the ranks' output slices (NCCL over
@@ -101,7 +121,6 @@ class PackedDecoderStack:
         hdl = symm_mem.rendezvous(buf, process_group)
         self._symm = (buf, hdl)
         self.epoch = torch.zeros((1,), dtype=torch.int32, device=self.device)
-        self.local_counts = torch.zeros((nlaunch,), dtype=torch.int32, device=self.device)
         self.fused_gather = []
         off, li_flat, prev_flag = flag_bytes, 0, None
         for li, ws in enumerate(widths):
@@ -117,7 +136,7 @@ class PackedDecoderStack:
                         g.y_peer[pr][i] = base + 2 * col
                         col += self.blocks[li][n]["N"]
                     g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * li_flat
-                g.local_count = self.local_counts.data_ptr() + 4 * li_flat
+                g.local_count = None
                 g.wait_flag = prev_flag
                 g.epoch = self.epoch.data_ptr()
                 prev_flag = buf.data_ptr() + 4 * li_flat
@@ -125,6 +144,7 @@ class PackedDecoderStack:
                 off += 2 * m * P * w
                 li_flat += 1
             self.fused_gather.append(row)
+        self._last_flag = prev_flag
         hdl.barrier()
         self.pg = None
 
@@ -144,6 +164,8 @@ class PackedDecoderStack:
         return tot
 
     def launches_per_step(self) -> int:
+        if self.program is not None:
+            return 1
         return (4 if self.fused else 7) * self.nlayers
 
     # ---- one token ------------------------------------------------------------------------------
@@ -152,6 +174,9 @@ class PackedDecoderStack:
                 "oweight": t["oweight_interleaved"], "bias": t.get("bias"), "N": t["N"], "y": y}
 
     def step_eager(self):
+        if self.program is not None:
+            self.program.run()
+            return self.result()
         m, r, G, h, f = self.batch, self.r, self.G, self.h, self.f
         lay = _lib.OW_INTERLEAVED
         fg = getattr(self, "fused_gather", None)
@@ -164,6 +189,10 @@ class PackedDecoderStack:
                 if fg is not None:
                     qeft_cuda.gemv_w4_multi_gather(x, [self._part(blk[n], None) for n in names], m, x.shape[-1], r, G,
                                                    fg[li][gi][0], ow_layout=lay, x_gather=gather, pdl=self.pdl)
+                    if li == len(self.blocks) - 1 and gi == len(self.groups) - 1:
+                        # the step's result is the gathered buffer of the last launch: order whatever follows in the stream
+                        # (the copy to the host) after the arrival of every rank's slice
+                        qeft_cuda.gather_wait(self._last_flag, self.epoch, self.world)
                     continue
                 if self.fused:
                     qeft_cuda.gemv_w4_multi(x, [self._part(blk[n], out[n]) for n in names], m, x.shape[-1], r, G,
@@ -175,6 +204,14 @@ class PackedDecoderStack:
                                           t["N"], x.shape[-1], G, ow_layout=lay, out=out[n], pdl=self.pdl,
                                           x_gather=gather)
                 self._gather(li, gi)
+        return self.result()
+
+    def result(self):
+        """The tensor a step produces: the last projection's output (the GATHERED [1, N] row when sharded)."""
+        if getattr(self, "fused_gather", None) is not None:
+            return self.fused_gather[-1][-1][1]
+        if self.pg is not None:
+            return self.grp_full[-1][-1].view(1, -1)
         return self.out[-1]["down"]
 
     def capture(self):
@@ -195,7 +232,7 @@ class PackedDecoderStack:
         if self.graph is None:
             return self.step_eager()
         self.graph.replay()
-        return self.out[-1]["down"]
+        return self.result()
 
     def step_from_host(self, x_host_h: torch.Tensor, x_host_f: torch.Tensor, y_host: torch.Tensor):
         """The end-to-end call: pinned host activations in, last projection's output back on the host."""

@@ -85,6 +85,38 @@ def replace_oweight(model, ckpt_wct):
     return model
 
 
+def prepare_for_finetune(model, gradient_checkpointing=False):
+    """Put a packed model into the state the reference fine-tunes it in -- what ``get_training_model`` does around
+    ``QuantLinear`` (qeft/finetune.py:372-379, 452-470, with peft's ``prepare_model_for_kbit_training`` :292-356):
+
+    * every ``QuantLinear``: ``set_kernel(training=True)`` (autograd path, ``QuantMatMulQEFT``) and ``set_for_wct()``
+      (packed weight frozen, outlier columns an fp32 trainable parameter);
+    * every other parameter frozen; parameters of modules whose name contains ``norm`` cast to fp32;
+    * only parameters with ``oweight`` in their name train;
+    * inputs of the embedding require grad when the model offers ``enable_input_require_grads`` (so that gradient
+      checkpointing has a differentiable path), and gradient checkpointing is switched on on request.
+    Returns the model; ``save_wctmodel`` then writes only the fine-tuned columns."""
+    for module in model.modules():
+        if isinstance(module, QuantLinear):
+            if not module.training or module.matmul is None:
+                module.set_kernel(training=True)
+            if not isinstance(module.oweight if module.outlierfeatures > 0 else None, torch.nn.Parameter):
+                module.set_for_wct()
+    for name, param in model.named_parameters():
+        param.requires_grad = False
+    for name, module in model.named_modules():
+        if "norm" in name:
+            module.to(torch.float32)
+    for name, param in model.named_parameters():
+        if "oweight" in name:
+            param.requires_grad = True
+    if hasattr(model, "enable_input_require_grads"):
+        model.enable_input_require_grads()
+    if gradient_checkpointing and hasattr(model, "gradient_checkpointing_enable"):
+        model.gradient_checkpointing_enable()
+    return model
+
+
 # --------------------------------------------------------------------------------------------------
 # column (output-feature) sharding of one packed layer -- SURVEY.md 8(e)
 # --------------------------------------------------------------------------------------------------

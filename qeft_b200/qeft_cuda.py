@@ -148,12 +148,40 @@ def gemv_w4_multi_gather(x, parts: Sequence[dict], m, k, r, group_size, gather, 
     _lib.check(st, "qeft_gemv_w4_multi_gather")
 
 
+def gather_wait(counter_ptr: int, epoch: torch.Tensor, nranks: int):
+    """Order the current stream after the arrival of every rank's slice of a fused-gather launch (include/qeft_b200.h)."""
+    with _on(epoch):
+        st = _lib.load().qeft_gather_wait(counter_ptr, _ptr(epoch), nranks, _stream(epoch))
+    _lib.check(st, "qeft_gather_wait")
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float16:
         return _lib.DT_F16
     if t.dtype == torch.bfloat16:
         return _lib.DT_BF16
     raise RuntimeError(f"expected scalar type Half or BFloat16 but found {t.dtype}")
+
+
+def _check_packed(what, x_dtype, qweight, scales, scaled_zeros, oweight, bias, K, group_size):
+    """The C ABI sees pointers only: check here what it cannot (the advisor's round-1 findings): the scale tables must
+    have the shape the kernel will index with ``group_size``, be fp16 like the checkpoint, and the dense outlier block
+    must have the activations' dtype (the kernels copy its bits unconverted)."""
+    N = qweight.shape[0] * 4
+    G = K if group_size in (-1, K) else group_size
+    if G <= 0 or K % G != 0:
+        raise RuntimeError(f"{what}: group_size {group_size} does not divide K = {K}")
+    for nm, t in (("scales", scales), ("scaled_zeros", scaled_zeros)):
+        if t.dtype != torch.float16:
+            raise RuntimeError(f"{what}: expected scalar type Half for {nm} but found {t.dtype}")
+        if tuple(t.shape) != (K // G, N) or not t.is_contiguous():
+            raise RuntimeError(f"{what}: {nm} must be a contiguous [{K // G}, {N}] tensor for group_size {G}, "
+                               f"found {tuple(t.shape)}")
+    if bias is not None and bias.dtype != torch.float16:
+        raise RuntimeError(f"{what}: expected scalar type Half for bias but found {bias.dtype}")
+    if oweight is not None and oweight.dtype != x_dtype:
+        raise RuntimeError(f"{what}: oweight is {oweight.dtype} but the activations are {x_dtype}; "
+                           "cast the outlier columns to the activations' dtype")
 
 
 def gemm_w4(x, qweight, scales, scaled_zeros, oweight, bias, *, group_size=128, out=None, pdl=None):
@@ -165,6 +193,7 @@ def gemm_w4(x, qweight, scales, scaled_zeros, oweight, bias, *, group_size=128, 
     M = x.numel() // K
     N = qweight.shape[0] * 4
     r = 0 if oweight is None else oweight.shape[1]
+    _check_packed("gemm_w4", x.dtype, qweight, scales, scaled_zeros, oweight, bias, K, group_size)
     if oweight is not None and not oweight.is_contiguous():
         oweight = oweight.contiguous()
     if out is None:
@@ -188,6 +217,7 @@ def gemm_w4_gather(x, qweight, scales, scaled_zeros, oweight, bias, gather, *, g
     M = x.numel() // K
     N = qweight.shape[0] * 4
     r = 0 if oweight is None else oweight.shape[1]
+    _check_packed("gemm_w4_gather", x.dtype, qweight, scales, scaled_zeros, oweight, bias, K, group_size)
     with _on(x):
         st = _lib.load().qeft_gemm_w4_gather(_ptr(x), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
                                              _ptr(bias), M, N, K, r, group_size, dt, _flags(pdl), C.byref(gather),
@@ -202,6 +232,9 @@ def gemm_w4_dx(dy, qweight, scales, scaled_zeros, oweight, K, *, group_size=128,
     N = dy.shape[-1]
     M = dy.numel() // N
     r = 0 if oweight is None else oweight.shape[1]
+    if qweight.shape[0] * 4 != N:
+        raise RuntimeError(f"gemm_w4_dx: dy has {N} features but qweight packs {qweight.shape[0] * 4} rows")
+    _check_packed("gemm_w4_dx", dy.dtype, qweight, scales, scaled_zeros, oweight, None, K, group_size)
     if out is None:
         out = torch.empty(dy.shape[:-1] + (K,), dtype=dy.dtype, device=dy.device)
     with _on(dy):
@@ -287,3 +320,76 @@ def interleave_oweight(oweight: torch.Tensor, out: Optional[torch.Tensor] = None
 
 def launch_count() -> int:
     return _lib.launch_count()
+
+
+# ----------------------------------------------------------------------------------------------
+# decode programs: a chain of dependent decode GEMVs as one persistent cooperative launch
+# ----------------------------------------------------------------------------------------------
+class DecodeProgram:
+    """A list of decode stages compiled into one persistent-kernel program (include/qeft_b200.h,
+    ``qeft_decode_program_*``; kernel ``csrc/decode_w4.cu``).
+
+    ``stages``: dicts with ``x`` (fp16 ``[m, K]``), ``parts`` (dicts with qweight, scales, scaled_zeros, oweight (plain
+    ``[N, r]``), optional bias, ``y`` (fp16 ``[m, N]``), N), ``K``, ``r``, ``G`` and optionally ``x_gather`` (int32 ``[K]``),
+    ``norm_weight`` / ``norm_eps`` (RMSNorm on the way in), ``epilogue`` ("swiglu" | "residual") and ``residual``.
+    Replaces the reference's per-projection launches of ``gemv_4bit_qeft`` (qeft/qlinear.py:251-263).  The tensors are
+    referenced, not copied: the program keeps them alive."""
+
+    _EPI = {None: _lib.EPI_NONE, "none": _lib.EPI_NONE, "swiglu": _lib.EPI_SWIGLU, "residual": _lib.EPI_RESIDUAL}
+
+    def __init__(self, stages: Sequence[dict], m: int = 1):
+        if not stages:
+            raise RuntimeError("DecodeProgram: no stages")
+        self.m = m
+        self._keep = []
+        arr = (_lib.DecodeStage * len(stages))()
+        dev = None
+        for i, st in enumerate(stages):
+            x = st["x"]
+            _need_cuda(x)
+            if x.dtype != torch.float16 or not x.is_contiguous():
+                raise RuntimeError("expected contiguous scalar type Half for in_feats")
+            dev = x.device if dev is None else dev
+            d = arr[i]
+            d.nparts = len(st["parts"])
+            if d.nparts > _lib.GEMV_MAX_PARTS:
+                raise RuntimeError("DecodeProgram: at most 4 projections per stage")
+            for j, p in enumerate(st["parts"]):
+                for k in ("qweight", "scales", "scaled_zeros"):
+                    _need_cuda(p[k])
+                ow = p.get("oweight")
+                if ow is not None and (ow.dtype != torch.float16 or not ow.is_contiguous()):
+                    raise RuntimeError("expected contiguous scalar type Half for oweight (plain [N, r] layout)")
+                d.parts[j] = _lib.GemvPart(_ptr(p["qweight"]), _ptr(p["scales"]), _ptr(p["scaled_zeros"]), _ptr(ow),
+                                           _ptr(p.get("bias")), _ptr(p.get("y")), p["N"])
+                self._keep.append(p)
+            d.K, d.r, d.G = st["K"], st["r"], st["G"]
+            d.x = _ptr(x)
+            d.x_gather = _ptr(st.get("x_gather"))
+            d.norm_weight = _ptr(st.get("norm_weight"))
+            d.norm_eps = float(st.get("norm_eps", 0.0))
+            d.epilogue = self._EPI[st.get("epilogue")]
+            d.residual = _ptr(st.get("residual"))
+            self._keep.append(st)
+        self.device = dev
+        self.nstages = len(stages)
+        handle = C.c_void_p()
+        with _on(stages[0]["x"]):
+            st = _lib.load().qeft_decode_program_create(arr, len(stages), m, C.byref(handle))
+        _lib.check(st, "qeft_decode_program_create")
+        self._h = handle
+
+    def run(self, begin: int = 0, end: Optional[int] = None):
+        end = self.nstages if end is None else end
+        with (_NO_GUARD if self.device.index in (None, torch.cuda.current_device()) else torch.cuda.device(self.device)):
+            st = _lib.load().qeft_decode_program_run(self._h, begin, end, 0, torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(st, "qeft_decode_program_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().qeft_decode_program_destroy(h)
+            except Exception:
+                pass
+            self._h = None

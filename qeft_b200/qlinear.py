@@ -86,15 +86,21 @@ def pack_oweight(oweight: torch.Tensor, interleave: int = 4) -> torch.Tensor:
 # autograd
 # --------------------------------------------------------------------------------------------------
 class QuantMatMulQEFT(torch.autograd.Function):
-    """``y = x . Wdense^T + bias`` with the outlier columns trainable (reference: qlinear.py:13-44)."""
+    """``y = x . Wdense^T + bias`` with the outlier columns trainable (reference: qlinear.py:13-44).
+
+    ``group_size`` is an extra trailing argument (the reference's kernels hard-code 128, gemm_cuda.cu:954): the
+    scales of a layer packed with another group size are indexed with it in forward, dX and nowhere else.
+    The launches are made WITHOUT programmatic dependent launch: ``oweight.to(fp16)`` runs as the kernel right
+    before the GEMM and the GEMM's dequant warps read ``oweight`` without waiting for the previous grid."""
 
     @staticmethod
-    def forward(ctx, x, oweight, qweight, scales, scaled_zeros, n_out, bias, name):
+    def forward(ctx, x, oweight, qweight, scales, scaled_zeros, n_out, bias, name, group_size=128):
         dtype = scales.dtype
         xh = x.to(dtype)
         ow_h = oweight.to(dtype)
-        y = qeft_cuda.gemm_w4(xh, qweight, scales, scaled_zeros, ow_h, bias)
+        y = qeft_cuda.gemm_w4(xh, qweight, scales, scaled_zeros, ow_h, bias, group_size=group_size, pdl=False)
         ctx.n_out = n_out
+        ctx.group_size = group_size
         ctx.in_dtype = x.dtype
         ctx.ow_dtype = oweight.dtype
         # only the r outlier activations are needed for dOW: keep a compact copy, not a view of x
@@ -109,21 +115,23 @@ class QuantMatMulQEFT(torch.autograd.Function):
         dy = grad_output.to(scales.dtype)
         grad_x = grad_ow = None
         if ctx.needs_input_grad[0]:
-            grad_x = qeft_cuda.gemm_w4_dx(dy, qweight, scales, scaled_zeros, ow_h, ctx.K).to(ctx.in_dtype)
+            grad_x = qeft_cuda.gemm_w4_dx(dy, qweight, scales, scaled_zeros, ow_h, ctx.K, group_size=ctx.group_size,
+                                          pdl=False).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
-            grad_ow = qeft_cuda.dow(dy, x_out, ctx.n_out).to(ctx.ow_dtype)
-        return grad_x, grad_ow, None, None, None, None, None, None
+            grad_ow = qeft_cuda.dow(dy, x_out, ctx.n_out, pdl=False).to(ctx.ow_dtype)
+        return grad_x, grad_ow, None, None, None, None, None, None, None
 
 
 class QuantMatMul(torch.autograd.Function):
     """No outlier columns (reference: qlinear.py:46-68)."""
 
     @staticmethod
-    def forward(ctx, x, qweight, scales, scaled_zeros, n_out, bias, name):
+    def forward(ctx, x, qweight, scales, scaled_zeros, n_out, bias, name, group_size=128):
         dtype = scales.dtype
-        y = qeft_cuda.gemm_w4(x.to(dtype), qweight, scales, scaled_zeros, None, bias)
+        y = qeft_cuda.gemm_w4(x.to(dtype), qweight, scales, scaled_zeros, None, bias, group_size=group_size, pdl=False)
         ctx.save_for_backward(qweight, scales, scaled_zeros)
         ctx.K = x.shape[-1]
+        ctx.group_size = group_size
         ctx.in_dtype = x.dtype
         return y
 
@@ -133,8 +141,8 @@ class QuantMatMul(torch.autograd.Function):
         grad_x = None
         if ctx.needs_input_grad[0]:
             grad_x = qeft_cuda.gemm_w4_dx(grad_output.to(scales.dtype), qweight, scales, scaled_zeros, None,
-                                          ctx.K).to(ctx.in_dtype)
-        return grad_x, None, None, None, None, None, None
+                                          ctx.K, group_size=ctx.group_size, pdl=False).to(ctx.in_dtype)
+        return grad_x, None, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -262,11 +270,12 @@ class QuantLinear(nn.Module):
             self.oweight_interleaved = pack_oweight(src.contiguous(), interleave=4).to(self.dtype)
 
     # ---- forwards --------------------------------------------------------------------------------
-    def _oweight_plain(self):
-        if getattr(self, "_ow_pad", 0):
-            return self.oweight_gemm
-        ow = self.oweight
-        return ow if ow.dtype == self.dtype else ow.to(self.dtype)
+    def _oweight_plain(self, dtype=None):
+        """The dense outlier block in the activations' dtype (the GEMM kernels take fp16 or bf16 operands and do not
+        convert: an fp16 block under bf16 activations would be read as bf16 bits)."""
+        dtype = self.dtype if dtype is None else dtype
+        ow = self.oweight_gemm if getattr(self, "_ow_pad", 0) else self.oweight
+        return ow if ow.dtype == dtype else ow.to(dtype)
 
     def _decode(self, x, seq_len, x_gather=None):
         r = self.outlierfeatures
@@ -282,11 +291,11 @@ class QuantLinear(nn.Module):
     def forward_outlier(self, x):
         if self._train_path():
             return self.matmul(x, self.oweight, self.qweight, self.scales, self.scaled_zeros,
-                               self.outlierfeatures, self.bias, self.name)
+                               self.outlierfeatures, self.bias, self.name, self.group_size)
         seq_len = x.numel() // x.shape[-1]
         if seq_len < self.GEMV_MAX_ROWS:
             return self._decode(x, seq_len)
-        return self.gemm(x, self.qweight, self.scales, self.scaled_zeros, self._oweight_plain(), self.bias,
+        return self.gemm(x, self.qweight, self.scales, self.scaled_zeros, self._oweight_plain(x.dtype), self.bias,
                          group_size=self.group_size)
 
     def forward_outlier_out_proj(self, x):
@@ -298,14 +307,14 @@ class QuantLinear(nn.Module):
         inputs = torch.index_select(x, -1, self.reorder_ids)
         if self._train_path():
             return self.matmul(inputs, self.oweight, self.qweight, self.scales, self.scaled_zeros,
-                               self.outlierfeatures, self.bias, self.name)
-        return self.gemm(inputs, self.qweight, self.scales, self.scaled_zeros, self._oweight_plain(), self.bias,
+                               self.outlierfeatures, self.bias, self.name, self.group_size)
+        return self.gemm(inputs, self.qweight, self.scales, self.scaled_zeros, self._oweight_plain(x.dtype), self.bias,
                          group_size=self.group_size)
 
     def forward_normal(self, x):
         if self._train_path():
             return self.matmul(x, self.qweight, self.scales, self.scaled_zeros, self.outlierfeatures, self.bias,
-                               self.name)
+                               self.name, self.group_size)
         seq_len = x.numel() // x.shape[-1]
         if seq_len < self.GEMV_MAX_ROWS:
             return self._decode(x, seq_len)

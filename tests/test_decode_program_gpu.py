@@ -1,0 +1,311 @@
+"""Parity of the persistent decode kernel ("decode programs", csrc/decode_w4.cu) against the CPU oracle, through
+the C ABI (qeft_decode_program_*).  Needs a B200.
+
+Tolerances.  north_star: "max relative error 1e-3".  Two forms are asserted for every case:
+  * max |err| / max |ref| <= 1e-3 (the form the round-1 tests used), and
+  * elementwise |err| <= 1e-3 |ref| + 2e-3 rms(ref): rtol covers a one-ulp flip of the fp16 result (2^-10), the
+    absolute term covers outputs that cancel to near zero: the oracle follows the reference and rounds every
+    dequantised weight to fp16 (fma.rn.f16, dequantize.cuh / gemv_cuda.cu:149-159) while this kernel multiplies
+    the exact s*q + sz, an error of 2^-11 |w| per weight = ~3e-4 rms(y) per output, uncorrelated with |y|.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-6))
+
+
+def assert_close(got, want, what=""):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.isfinite(got).all(), what
+    e = rel_err(got, want)
+    assert e <= REL_TOL, (what, e)
+    rms = float(np.sqrt(np.mean(want ** 2))) + 1e-12
+    bad = np.abs(got - want) > 1e-3 * np.abs(want) + 2e-3 * rms
+    assert not bad.any(), (what, int(bad.sum()), float(np.max(np.abs(got - want)) / rms))
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def part_of(L, y):
+    p = {"qweight": dev(L["qweight"]), "scales": dev(L["scales"]), "scaled_zeros": dev(L["scaled_zeros"]),
+         "N": L["N"], "y": y}
+    if L["r"] > 0:
+        p["oweight"] = dev(L["oweight"])
+    if "bias" in L:
+        p["bias"] = dev(L["bias"])
+    return p
+
+
+def make_stage(layers, x_t, m, **kw):
+    """One stage over `layers` (same K, r, G) reading the device tensor x_t; outputs are allocated here."""
+    L0 = layers[0]
+    ys = [torch.full((m, L["N"]), float("nan"), dtype=torch.float16, device="cuda") for L in layers]
+    st = {"x": x_t, "parts": [part_of(L, y) for L, y in zip(layers, ys)], "K": L0["K"], "r": L0["r"], "G": L0["G"]}
+    st.update(kw)
+    return st, ys
+
+
+def ref_forward(L, x, ids=None):
+    return oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L.get("oweight"), L.get("bias"),
+                          group_size=L["G"], reorder_ids=ids)
+
+
+@pytest.mark.parametrize("N,K,r,G", [
+    (16, 128, 0, 128), (8, 64, 0, 64), (24, 256, 32, 128), (32, 256, 128, 128), (40, 384, 64, 128),
+    (64, 512, 96, 512), (64, 512, 128, 256), (72, 1024, 288, 128), (256, 640, 96, 128), (128, 1024, 128, 128),
+    (4096, 4096, 128, 128), (1024, 8192, 128, 128), (12288, 256, 64, 128),
+])
+@pytest.mark.parametrize("m", [1, 2])
+def test_single_stage_matches_oracle(N, K, r, G, m):
+    from qeft_b200 import qeft_cuda
+    L = oracle.synth_layer(N, K, r=r, G=G, seed=N + K + r, bias=True)
+    x = np.random.default_rng(m).standard_normal((m, K)).astype(np.float16)
+    st, ys = make_stage([L], dev(x), m)
+    prog = qeft_cuda.DecodeProgram([st], m=m)
+    prog.run()
+    torch.cuda.synchronize()
+    assert_close(ys[0].cpu().numpy(), ref_forward(L, x), (N, K, r, G, m))
+
+
+@pytest.mark.parametrize("shape", [(11008, 4096), (4096, 11008)])
+def test_llama7b_ffn_shapes(shape):
+    from qeft_b200 import qeft_cuda
+    N, K = shape
+    L = oracle.synth_layer(N, K, seed=5)
+    x = np.random.default_rng(1).standard_normal((1, K)).astype(np.float16)
+    st, ys = make_stage([L], dev(x), 1)
+    prog = qeft_cuda.DecodeProgram([st])
+    prog.run()
+    torch.cuda.synchronize()
+    assert_close(ys[0].cpu().numpy(), ref_forward(L, x), shape)
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_multi_part_stage_and_old_kernel(m):
+    """q/k/v in one stage; also against the round-1 GEMV kernel (qeft_gemv_w4_multi) on the same device tensors."""
+    from qeft_b200 import _lib, qeft_cuda
+    K, r, G = 1024, 128, 128
+    Ls = [oracle.synth_layer(N, K, r=r, seed=20 + i, bias=(i == 1)) for i, N in enumerate((256, 64, 72))]
+    x = np.random.default_rng(4).standard_normal((m, K)).astype(np.float16)
+    xd = dev(x)
+    st, ys = make_stage(Ls, xd, m)
+    prog = qeft_cuda.DecodeProgram([st], m=m)
+    prog.run()
+    old = qeft_cuda.gemv_w4_multi(xd, [{k: v for k, v in p.items() if k != "y"} for p in st["parts"]], m, K, r, G,
+                                  ow_layout=_lib.OW_PLAIN, pdl=False)
+    torch.cuda.synchronize()
+    for L, y, yo in zip(Ls, ys, old):
+        assert_close(y.cpu().numpy(), ref_forward(L, x), L["N"])
+        assert_close(y.cpu().numpy(), yo.cpu().numpy().astype(np.float64), ("old", L["N"]))
+
+
+def test_o_proj_gather_stage():
+    from qeft_b200 import qeft_cuda
+    N, K, r = 256, 512, 128
+    L = oracle.synth_layer(N, K, r=r, seed=11, o_proj=True)
+    ids = oracle.sparse_to_dense_ids(L["outlieridx"], K)
+    for m in (1, 2):
+        x = np.random.default_rng(2 + m).standard_normal((m, K)).astype(np.float16)
+        st, ys = make_stage([L], dev(x), m, x_gather=dev(ids.astype(np.int32)))
+        prog = qeft_cuda.DecodeProgram([st], m=m)
+        prog.run()
+        torch.cuda.synchronize()
+        assert_close(ys[0].cpu().numpy(), ref_forward(L, x, ids), m)
+        # identical to the un-fused path on pre-gathered input
+        st2, ys2 = make_stage([L], dev(np.take(x, ids, axis=-1)), m)
+        qeft_cuda.DecodeProgram([st2], m=m).run()
+        torch.cuda.synchronize()
+        assert np.array_equal(ys[0].cpu().numpy().view(np.uint16), ys2[0].cpu().numpy().view(np.uint16))
+
+
+def test_wide_dynamic_range_activations():
+    """x with 2^24 of dynamic range inside single 128-column blocks and between blocks (the int8-digit representation
+    is a 30-bit fixed point per activation row: |err| <= max|x| 2^-30 per element)."""
+    from qeft_b200 import qeft_cuda
+    N, K, r = 128, 1024, 128
+    L = oracle.synth_layer(N, K, r=r, seed=77)
+    rng = np.random.default_rng(9)
+    for m in (1, 2):
+        x = rng.standard_normal((m, K)).astype(np.float32)
+        x *= np.exp2(rng.integers(-12, 12, size=(m, K))).astype(np.float32)
+        x[:, 5] = 30000.0                       # one massive activation per row
+        x[:, 300:310] = 6e-5                    # and fp16 subnormal-range ones
+        x = x.astype(np.float16)
+        st, ys = make_stage([L], dev(x), m)
+        qeft_cuda.DecodeProgram([st], m=m).run()
+        torch.cuda.synchronize()
+        assert_close(ys[0].cpu().numpy(), ref_forward(L, x), m)
+    # all-zero input
+    x = np.zeros((1, K), np.float16)
+    st, ys = make_stage([L], dev(x), 1)
+    qeft_cuda.DecodeProgram([st]).run()
+    torch.cuda.synchronize()
+    assert np.all(ys[0].cpu().numpy() == 0)
+
+
+def _chain_layers(dims, r, seed):
+    return [oracle.synth_layer(dims[i + 1], dims[i], r=r, seed=seed + i, bias=(i % 2 == 0)) for i in range(len(dims) - 1)]
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_chained_stages_one_launch(m):
+    """Stage i+1 reads what stage i wrote (gpu-scope barrier inside one cooperative launch); run repeatedly, in
+    sub-ranges, and replayed from a CUDA graph."""
+    from qeft_b200 import qeft_cuda
+    dims = [512, 1280, 256, 2048, 384]
+    Ls = _chain_layers(dims, 128, 40)
+    x = np.random.default_rng(5).standard_normal((m, dims[0])).astype(np.float16)
+    xd = dev(x)
+    stages, outs = [], []
+    cur = xd
+    for L in Ls:
+        st, ys = make_stage([L], cur, m)
+        stages.append(st)
+        outs.append(ys[0])
+        cur = ys[0]
+    prog = qeft_cuda.DecodeProgram(stages, m=m)
+
+    def check():
+        torch.cuda.synchronize()
+        inp = x
+        for L, y in zip(Ls, outs):
+            got = y.cpu().numpy()
+            assert_close(got, ref_forward(L, inp), L["N"])
+            inp = got                                     # the next stage must have read exactly these bits
+
+    prog.run()
+    check()
+    first = [y.clone() for y in outs]
+    for y in outs:
+        y.fill_(float("nan"))
+    prog.run()                                            # second run: barrier words carry over
+    check()
+    for a, b in zip(first, outs):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))     # deterministic
+    for y in outs:
+        y.fill_(float("nan"))
+    prog.run(0, 2)
+    prog.run(2, 4)                                        # sub-ranges
+    check()
+    # CUDA graph replay of the cooperative launch
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        prog.run()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        prog.run()
+    for y in outs:
+        y.fill_(float("nan"))
+    for _ in range(3):
+        g.replay()
+    check()
+    for a, b in zip(first, outs):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+def _rmsnorm_ref(x, w, eps):
+    """HF LlamaRMSNorm / the reference's FT layernorm (kernel/layernorm/layernorm.cu:25-51): fp32 statistics, the
+    normalised value rounded to fp16, then multiplied by the fp16 weight."""
+    xf = x.astype(np.float32)
+    rs = 1.0 / np.sqrt(np.mean(xf * xf, axis=-1, keepdims=True) + eps)
+    return (w.astype(np.float16) * (xf * rs).astype(np.float16)).astype(np.float16)
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_rmsnorm_prologue(m):
+    from qeft_b200 import qeft_cuda
+    N, K, r = 192, 1024, 128
+    L = oracle.synth_layer(N, K, r=r, seed=61)
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal((m, K)) * 3).astype(np.float16)
+    w = (1 + 0.1 * rng.standard_normal(K)).astype(np.float16)
+    eps = 1e-5
+    st, ys = make_stage([L], dev(x), m, norm_weight=dev(w), norm_eps=eps)
+    qeft_cuda.DecodeProgram([st], m=m).run()
+    torch.cuda.synchronize()
+    xn = _rmsnorm_ref(x, w, eps)
+    assert_close(ys[0].cpu().numpy(), ref_forward(L, xn), m)
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_swiglu_and_residual_epilogues(m):
+    from qeft_b200 import qeft_cuda
+    h, f, r = 512, 1408, 128
+    Lg = oracle.synth_layer(f, h, r=r, seed=71)
+    Lu = oracle.synth_layer(f, h, r=r, seed=72, bias=True)
+    Ld = oracle.synth_layer(h, f, r=r, seed=73)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((m, h)).astype(np.float16)
+    res = rng.standard_normal((m, h)).astype(np.float16)
+    xd, resd = dev(x), dev(res)
+    st1, ys1 = make_stage([Lg, Lu], xd, m, epilogue="swiglu")
+    st2, ys2 = make_stage([Ld], ys1[0], m, epilogue="residual", residual=resd)
+    qeft_cuda.DecodeProgram([st1, st2], m=m).run()
+    torch.cuda.synchronize()
+    gate = ref_forward(Lg, x).astype(np.float32)
+    up = ref_forward(Lu, x)
+    act = ((gate / (1 + np.exp(-gate))).astype(np.float16) * up).astype(np.float16)
+    got_act = ys1[0].cpu().numpy()
+    assert_close(got_act, act, "swiglu")
+    want = (res.astype(np.float32) + ref_forward(Ld, got_act).astype(np.float32)).astype(np.float16)
+    assert_close(ys2[0].cpu().numpy(), want, "residual")
+
+
+def test_llama7b_block_program():
+    """One Llama-2-7B-shaped decoder block as a 4-stage program (qkv, o with the reorder gather, gate/up, down) from
+    fixed activations, against the oracle on every projection."""
+    from qeft_b200 import qeft_cuda
+    h, f, r, G = 4096, 11008, 128, 128
+    rng = np.random.default_rng(3)
+    xh = rng.standard_normal((1, h)).astype(np.float16)
+    xf = rng.standard_normal((1, f)).astype(np.float16)
+    xhd, xfd = dev(xh), dev(xf)
+    names = [("q", h, h), ("k", h, h), ("v", h, h), ("o", h, h), ("gate", f, h), ("up", f, h), ("down", h, f)]
+    Ls = {n: oracle.synth_layer(N, K, r=r, G=G, seed=100 + i, o_proj=(n == "o")) for i, (n, N, K) in enumerate(names)}
+    ids = oracle.sparse_to_dense_ids(Ls["o"]["outlieridx"], h)
+    s0, y0 = make_stage([Ls["q"], Ls["k"], Ls["v"]], xhd, 1)
+    s1, y1 = make_stage([Ls["o"]], xhd, 1, x_gather=dev(ids.astype(np.int32)))
+    s2, y2 = make_stage([Ls["gate"], Ls["up"]], xhd, 1)
+    s3, y3 = make_stage([Ls["down"]], xfd, 1)
+    prog = qeft_cuda.DecodeProgram([s0, s1, s2, s3])
+    prog.run()
+    torch.cuda.synchronize()
+    for n, y in zip(("q", "k", "v"), y0):
+        assert_close(y.cpu().numpy(), ref_forward(Ls[n], xh), n)
+    assert_close(y1[0].cpu().numpy(), ref_forward(Ls["o"], xh, ids), "o")
+    for n, y in zip(("gate", "up"), y2):
+        assert_close(y.cpu().numpy(), ref_forward(Ls[n], xh), n)
+    assert_close(y3[0].cpu().numpy(), ref_forward(Ls["down"], xf), "down")
+
+
+def test_program_argument_errors():
+    from qeft_b200 import qeft_cuda
+    L = oracle.synth_layer(64, 256, r=64, seed=1)
+    x = dev(np.zeros((1, 256), np.float16))
+    st, _ = make_stage([L], x, 1)
+    with pytest.raises(RuntimeError):
+        qeft_cuda.DecodeProgram([st], m=3)                 # batch > 2: the GEMV entry handles those
+    bad = dict(st, K=200)
+    with pytest.raises(RuntimeError):
+        qeft_cuda.DecodeProgram([bad])
+    bad = dict(st, epilogue="swiglu")
+    with pytest.raises(RuntimeError):
+        qeft_cuda.DecodeProgram([bad])                     # needs exactly {gate, up}
