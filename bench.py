@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the oracle's CPU port even when "
                                                              "the reference's own kernels (oracle/_ref) are available")
     ap.add_argument("--no-gemm", action="store_true", help="skip the prefill GEMM / backward extras (M=2048 TFLOP/s)")
+    ap.add_argument("--no-program", action="store_true",
+                    help="N = 1: the round-1 chain of 4 x layers PDL launches instead of the persistent decode program")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the gathered-output parity check before timing")
     return ap.parse_args()
 
 
@@ -112,12 +115,12 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(avg_alg_bytes_per_launch):
+def ncu_traffic(avg_alg_bytes_per_launch, kernel="gemv"):
     """DRAM bytes per launch from the committed `ncu --set full` capture of the dominant kernel
-    (profiles/gemv_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum and the algorithmic bytes of the
-    profiled launch).  The bench's launches have four shapes, so the per-launch figure reported beside `achieved`
-    is the measured traffic / algorithmic ratio applied to this run's average algorithmic bytes per launch."""
-    p = os.path.join(ROOT, "profiles", "gemv_traffic.json")
+    (profiles/<kernel>_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum and the algorithmic bytes of the
+    profiled launch): the measured traffic / algorithmic ratio applied to this run's algorithmic bytes per launch.
+    It is a figure FROM THE PROFILE, not of this run (bench.py never runs under ncu)."""
+    p = os.path.join(ROOT, "profiles", f"{kernel}_traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
@@ -284,6 +287,76 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def sharded_parity_check(stack, world, rank, gather_mode):
+    """N > 1, before the timed loop: one eager step in the active exchange mode, then EVERY rank checks the gathered
+    buffer of all four launch groups of the first and of the last decoder block against
+      (a) this rank's local kernel outputs all-gathered by NCCL (same kernel, same row partition): bit-equal, and
+      (b) the UNSHARDED kernel (qeft_gemv_w4_multi on the weights of all ranks, gathered here for the check, same x):
+          equal to one fp16 ulp (the row partition changes the fp32 summation order of a row's K-slices).
+    Returns {"groups": n, "ok": bool, ...}; the caller exits non-zero when not ok."""
+    import torch
+    import torch.distributed as dist
+
+    from qeft_b200 import _lib, qeft_cuda
+
+    stack.step_eager()
+    torch.cuda.synchronize()
+    dist.barrier()
+    m, r, G = stack.batch, stack.r, stack.G
+    checked, bad_a, bad_b, worst_ulp = 0, 0, 0, 0.0
+
+    def gather_cat(t, dim):
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        return torch.cat(parts, dim=dim).contiguous()
+
+    for li in sorted({0, stack.nlayers - 1}):
+        blk = stack.blocks[li]
+        for gi, names in enumerate(stack.groups):
+            x = stack.x_f if names[0] == "down" else stack.x_h
+            gather = blk["o"].get("reorder_ids32") if names[0] == "o" else None
+            if gather_mode == "fused":
+                got = stack.fused_gather[li][gi][1].view(world, -1)
+            else:
+                got = stack.grp_full[li][gi]
+            # (a) local kernel + NCCL
+            local = qeft_cuda.gemv_w4_multi(x, [stack._part(blk[n], None) for n in names], m, x.shape[-1], r, G,
+                                            ow_layout=_lib.OW_INTERLEAVED, x_gather=gather, pdl=False)
+            loc = torch.cat([y.reshape(1, -1) for y in local], dim=1).contiguous()
+            want_a = torch.empty((world, loc.shape[1]), dtype=loc.dtype, device=loc.device)
+            dist.all_gather_into_tensor(want_a.view(-1), loc.view(-1))
+            bad_a += int(not torch.equal(want_a, got))
+            # (b) the unsharded kernel on everybody's weights
+            full_parts = []
+            for n in names:
+                t = blk[n]
+                full_parts.append({"qweight": gather_cat(t["qweight"], 0), "scales": gather_cat(t["scales"], 1),
+                                   "scaled_zeros": gather_cat(t["scaled_zeros"], 1),
+                                   "oweight": gather_cat(t["oweight_interleaved"], 0), "N": t["N"] * world})
+            full = qeft_cuda.gemv_w4_multi(x, full_parts, m, x.shape[-1], r, G, ow_layout=_lib.OW_INTERLEAVED,
+                                           x_gather=gather, pdl=False)
+            torch.cuda.synchronize()
+            want_b = torch.cat([torch.cat([y.reshape(-1)[p * blk[n]["N"]:(p + 1) * blk[n]["N"]] for y, n in zip(full, names)])
+                                for p in range(world)]).view(world, -1)
+            d = (want_b.float() - got.float()).abs()
+            ulp = torch.clamp(want_b.float().abs(), min=2.0 ** -14) * 2.0 ** -10      # one fp16 ulp at |want|
+            worst = float((d / ulp).max())
+            worst_ulp = max(worst_ulp, worst)
+            bad_b += int(worst > 1.0)
+            del full_parts, full
+            checked += 1
+    torch.cuda.empty_cache()
+    res = torch.tensor([bad_a, bad_b], dtype=torch.int64, device="cuda")
+    dist.all_reduce(res, op=dist.ReduceOp.SUM)
+    wu = torch.tensor([worst_ulp], dtype=torch.float64, device="cuda")
+    dist.all_reduce(wu, op=dist.ReduceOp.MAX)
+    return {"groups": checked, "ok": bool(res.sum().item() == 0), "mode": gather_mode,
+            "mismatch_vs_local_plus_nccl": int(res[0].item()), "groups_off_by_more_than_1ulp_vs_unsharded": int(res[1].item()),
+            "worst_ulp_vs_unsharded": wu.item(),
+            "what": "all 4 launch groups of the first and last block, every rank; bit-equal to local kernel + NCCL all-gather, "
+                    "<= 1 fp16 ulp from the unsharded kernel on the gathered weights"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -313,6 +386,17 @@ def run_ours(args):
                 stack.fused_gather = None
         if gather_mode == "nccl":
             stack.enable_allgather(dist.group.WORLD)
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = sharded_parity_check(stack, world, rank, gather_mode)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_checked": parity,
+                                  "error": "gathered outputs differ from the unsharded kernel"}), flush=True)
+            os._exit(3)
+    use_program = world == 1 and not args.no_program and not args.no_fused and args.batch <= 2
+    if use_program:
+        stack.enable_program()       # one persistent cooperative launch per token (csrc/decode_w4.cu)
     if not args.no_graph:
         stack.capture()
 
@@ -371,6 +455,38 @@ def run_ours(args):
     nbytes_all = tot.item()
 
     extra = {}
+    if use_program and rank == 0:
+        # beside the headline: the same token (a) as one launch per decoder block (4 stages each: where attention would sit
+        # between launches in a full decoder) and (b) as the round-1 chain of 4 x layers PDL launches in a CUDA graph
+        def time_steps(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        prog, nl = stack.program, stack.nlayers
+
+        def per_block():
+            for li in range(nl):
+                prog.run(4 * li, 4 * li + 4)
+
+        ms_blk = time_steps(per_block, args.steps)
+        stack.program, stack.graph = None, None
+        stack.capture()
+        ms_chain = time_steps(stack.step, args.steps)
+        stack.graph, stack.program = None, prog
+        nb1 = stack.algorithmic_bytes_per_step()
+        extra["decode_variants"] = {
+            "one_launch_per_block": {"launches_per_token": nl, "ms_per_token": ms_blk, "GBps": nb1 / ms_blk / 1e6},
+            "round1_launch_chain": {"launches_per_token": 4 * nl, "ms_per_token": ms_chain, "GBps": nb1 / ms_chain / 1e6,
+                                    "what": "gemv_w4_kernel, 4 PDL launches per block, CUDA graph (round-1 headline path)"},
+        }
     if not args.no_gemm and rank == 0 and world == 1:
         del stack
         torch.cuda.empty_cache()
@@ -401,25 +517,35 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {
                 "workload": (f"llama2-{model} decode b{args.batch}: {workload_layers} decoder blocks x 7 packed QuantLinear "
-                             f"(w4 g128 r128) = {launches_per_step} GEMV launches/token"
+                             f"(w4 g128 r128) = "
+                             + (f"{4 * workload_layers} dependent GEMV stages/token in ONE persistent cooperative launch "
+                                f"(gpu-scope barrier between stages)" if use_program else f"{launches_per_step} GEMV launches/token")
                              + (f", column-sharded over {world} ranks, all-gather "
                                 + ("fused into the GEMV epilogue (peer stores over NVLink)" if gather_mode == "fused" else "by NCCL")
                                 if world > 1 else "")),
                 "algorithmic_bytes_per_step": int(nbytes_all), "l2_policy": "inputs larger than L2 (3.7 GB of weights streamed per step)",
                 "cuda_graph": workload_graph, "fused_qkv_gateup": workload_fused, "pdl": workload_pdl,
-                "layers": workload_layers,
+                "layers": workload_layers, "persistent_program": bool(use_program),
             },
             "decode_tok_s": args.batch * 1e3 / ms_step,
+            "decode_tok_s_note": "packed linears only (224 QuantLinear of the 32 blocks fed from fixed activation buffers); "
+                                 "attention, norms, embeddings and lm_head are not part of this path (SURVEY.md 8)",
             "clocks": clocks,
             "e2e": {"value": gbs_e2e, "unit": "GB/s", "tok_s": args.batch * 1e3 / (ms_e2e / args.steps),
                     "h2d_bytes_per_step": int(xh.numel() * 2 + xf.numel() * 2), "d2h_bytes_per_step": int(yh.numel() * 2)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
-                         "frac_of_nominal_8TBs": per_gpu / 8000.0, "peak_source": peak_src, "kernel": "gemv_w4_kernel",
-                         "traffic": ncu_traffic(nbytes_all / world / launches_per_step),
-                         "traffic_unit": "bytes per launch (ncu dram read+write of the profiled launch, scaled by algorithmic bytes)",
+                         "frac_of_nominal_8TBs": per_gpu / 8000.0, "peak_source": peak_src,
+                         "kernel": "decode_w4_kernel" if use_program else "gemv_w4_kernel",
+                         "traffic": ncu_traffic(nbytes_all / world / launches_per_step, "decode" if use_program else "gemv"),
+                         "traffic_unit": "bytes per launch = traffic_ratio_from_profile x algorithmic bytes of this run's launch "
+                                         "(ratio: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full "
+                                         "capture of this kernel / its algorithmic bytes; profiles/*_traffic.json)",
+                         "traffic_ratio_from_profile": ncu_traffic(1.0, "decode" if use_program else "gemv"),
                          "algorithmic_bytes_per_launch": nbytes_all / world / launches_per_step},
         }
+        if parity is not None:
+            line["parity_checked"] = parity
         if args.layers is not None:
             line["config"]["INVALID"] = "reduced layer count (debug run)"
         if world == 1 and not args.no_cpu_baseline:

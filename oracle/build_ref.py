@@ -133,7 +133,7 @@ def build(verbose: bool = True) -> str | None:
 # repo's `qeft_cuda` shim on the GPU box, where /root/reference does not exist.  baseline/_ref/ is git-ignored (the
 # files never enter the history) and travels with gpurun, like oracle/_ref/.
 PY_STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
-PY_FILES = ["qeft/__init__.py", "qeft/qlinear.py", "qeft/reorder.py"]
+PY_FILES = ["qeft/__init__.py", "qeft/qlinear.py", "qeft/reorder.py", "qeft/utils/__init__.py", "qeft/utils/misc.py"]
 
 
 def stage_reference_python() -> str | None:

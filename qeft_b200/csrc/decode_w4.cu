@@ -38,9 +38,15 @@
 namespace qeft {
 
 constexpr int kDWarps = 16;
-constexpr int kDThreads = kDWarps * 32;
-constexpr int kSlotScale = 1024;              // byte offset of the unit's scales (32 B) and scaled zeros (32 B)
-constexpr int kSlot = 1088;                   // bytes per ring slot
+constexpr int kDThreads = kDWarps * 32;       // consumer threads; one more warp only fills the ring
+constexpr int kDBlock = kDThreads + 32;
+#ifndef QEFT_DEC_STAGGER
+#define QEFT_DEC_STAGGER 16                     // qweight-row areas 16 bytes apart (mod 128): conflict-free ldmatrix (measured: bulk copies do not care)
+#endif
+constexpr int kKB = 32;                       // 128-column steps per tile-block
+constexpr int kQArea = kKB * 256 + QEFT_DEC_STAGGER;   // slot bytes per qweight row: 8 KB of packed words (+ optional stagger)
+constexpr int kSlotW = 4 * kQArea;            // the four qweight rows of a 16-row tile
+constexpr int kSideSteps = kKB * 16;           // side bytes per qweight row and block: 16 per step (+ 8 r for the outlier columns)
 constexpr size_t kDSmemMax = 227 * 1024;
 
 struct DecPart {
@@ -50,9 +56,37 @@ struct DecPart {
   const __half* ow;       // plain [N, r]
   const __half* bias;
   __half* y;              // [m, N]
+  const uint8_t* side;    // decode side table (built at program creation), per qweight row: [steps][scales of its 4 rows |
+                          // scaled zeros of its 4 rows] then the fp16 outlier columns in MMA-fragment order
+  int side_q;             // bytes per qweight row of `side`
   int N;
   int q_begin;            // first qweight row of this part in the stage-wide numbering (plain stages)
 };
+
+// Builds one part's side table: side[q][s] = {scales[grp(s)][4q..4q+3], szeros[grp(s)][4q..4q+3]} (16 bytes per 128-column
+// step s), followed by the outlier columns of rows 4q..4q+3 as HMMA m16n8k16 A fragments: unit u (16 columns), lane-row
+// gi (rows 4q+2gi, 4q+2gi+1), lane-column t: {row a cols 2t,2t+1 | row b same | row a cols 8+2t,9+2t | row b same} (16 bytes).
+// A one-time re-layout of 5 % + 11 % of the layer's bytes, the counterpart of the reference's `oweight_interleaved`
+// (qeft/qlinear.py:70-79, 213): every block of the kernel then needs ONE contiguous side copy per qweight row.
+__global__ void dec_build_side_kernel(const __half* scales, const __half* szeros, const __half* ow, uint8_t* side, int N, int r,
+                                      int g128, int nsteps, int side_q) {
+  const int q = blockIdx.x;
+  uint8_t* dst = side + (size_t)q * side_q;
+  for (int i = threadIdx.x; i < nsteps * 8; i += blockDim.x) {
+    const int s = i >> 3, e = i & 7;
+    const int grp = g128 == 1 ? s : (g128 == 0 ? 0 : s / g128);
+    const __half* src = (e < 4 ? scales : szeros) + (size_t)grp * N + 4 * q + (e & 3);
+    reinterpret_cast<__half*>(dst)[s * 8 + e] = *src;
+  }
+  __half* o = reinterpret_cast<__half*>(dst + (size_t)nsteps * 16);
+  for (int i = threadIdx.x; i < (r >> 4) * 64; i += blockDim.x) {
+    const int u = i >> 6, w = i & 63;                        // 64 halves per unit
+    const int gi = w >> 5, t = (w >> 3) & 3, e = w & 7;      // e: {a0.lo, a0.hi, a1.lo, a1.hi, a2.lo, a2.hi, a3.lo, a3.hi}
+    const int row = 4 * q + 2 * gi + ((e >> 1) & 1);
+    const int col = 16 * u + 2 * t + (e & 1) + ((e >> 2) & 1) * 8;
+    o[i] = ow[(size_t)row * r + col];
+  }
+}
 
 struct DecStage {
   DecPart part[QEFT_GEMV_MAX_PARTS];
@@ -70,9 +104,11 @@ struct DecStage {
 };
 
 struct DecLayout {            // shared-memory carve-up (bytes from the start of dynamic shared memory)
-  int xdig, xsum, xo, part, misc;
-  int max_touch;              // tiles a warp's run can touch
-  unsigned long long* stamps; // debug (QEFT_DECODE_STAMPS): [stage][4 CTAs][4] globaltimer values, or null
+  int nslots, slot;           // ring at offset 0: nslots slots of `slot` bytes: [4 x kQArea packed words][4 x sarea side bytes]
+  int slot_s, sarea;
+  int xdig, xsum, xo, part, part_bytes, misc;
+  int debug;                  // QEFT_DECODE_DEBUG bit mask (bisecting switches; results are WRONG when set)
+  unsigned long long* stamps; // debug (QEFT_DECODE_STAMPS): [stage][4 CTAs][8] globaltimer values, or null
 };
 
 __device__ __forceinline__ void dec_stamp(const DecLayout& L, int s, int i) {
@@ -81,7 +117,7 @@ __device__ __forceinline__ void dec_stamp(const DecLayout& L, int s, int i) {
     if (c >= 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      L.stamps[((size_t)s * 4 + c) * 4 + i] = t;
+      L.stamps[((size_t)s * 4 + c) * 8 + i] = t;
     }
   }
 }
@@ -148,24 +184,6 @@ __device__ __forceinline__ void d_imma0(int (&d)[4], uint32_t a0, uint32_t a1, u
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 
-struct DecRun { int qa, nq, U, ns, u0, u1, ntiles; };
-
-// this CTA's qweight rows of a stage and one warp's run of (tile, unit) pairs
-__device__ __forceinline__ DecRun dec_run(const DecStage* S, int cta, int ncta, int warp) {
-  DecRun R;
-  const int al = S->epilogue == QEFT_EPI_SWIGLU ? 2 : 1;     // SwiGLU: gate / up qweight rows alternate, CTAs own pairs
-  const long Qa = S->total_q / al;
-  R.qa = al * (int)((Qa * cta) / ncta);
-  R.nq = al * (int)((Qa * (cta + 1)) / ncta) - R.qa;
-  R.ntiles = (R.nq + 3) >> 2;
-  R.ns = S->nsteps;
-  R.U = R.ns + S->nou;
-  const int TU = R.ntiles * R.U;
-  R.u0 = (warp * TU) / kDWarps;
-  R.u1 = ((warp + 1) * TU) / kDWarps;
-  return R;
-}
-
 // stage-wide qweight row -> (part, part-local qweight row)
 __device__ __forceinline__ void dec_locate(const DecStage* S, int vq, int& pi, int& lq) {
   if (S->epilogue == QEFT_EPI_SWIGLU) { pi = vq & 1; lq = vq >> 1; return; }
@@ -176,151 +194,195 @@ __device__ __forceinline__ void dec_locate(const DecStage* S, int vq, int& pi, i
   lq = vq - S->part[pi].q_begin;
 }
 
-// copies with the PTX "ignore-src" predicate: when ign != 0 nothing is read and the destination is zero-filled
-__device__ __forceinline__ void d_cp16z(uint32_t dst, const void* src, int ign) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
-               ::"r"(dst), "l"(src), "r"(ign) : "memory");
+// ---- mbarrier / bulk-copy / ldmatrix helpers ---------------------------------------------------------------
+__device__ __forceinline__ void d_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// the same for 8 bytes, issued only by lanes with act != 0
-__device__ __forceinline__ void d_cp8z_if(uint32_t dst, const void* src, int act, int ign) {
-  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %3, 0;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-               "@q cp.async.ca.shared.global [%0], [%1], 8, p;\n\t}"
-               ::"r"(dst), "l"(src), "r"(act), "r"(ign) : "memory");
+__device__ __forceinline__ void d_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void d_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\t"
+               "bra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool d_mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// 1-D bulk copy global -> shared by the TMA engine (UBLKCP): no LSU issue slots, completion on the mbarrier
+__device__ __forceinline__ void d_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// arrive on the mbarrier when all cp.async issued so far by this thread have landed (no pending-count increment)
+__device__ __forceinline__ void d_cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void d_cp16p(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void d_cp8p(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void d_ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
 
-// D: ring depth (units per warp).  M: batch rows (1 or 2); the B fragment's 8 columns are M x 4 digit columns.
-template <int D, int M>
-__global__ void __launch_bounds__(kDThreads, 1)
+// barrier of the 16 consumer warps (the producer warp never joins)
+__device__ __forceinline__ void d_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kDThreads) : "memory"); }
+
+struct DecTiles { int qa, nq, ntiles; };
+
+// this CTA's qweight rows of a stage (balance to one qweight row), cut into 16-row tiles
+__device__ __forceinline__ DecTiles dec_tiles(const DecStage* S, int cta, int ncta) {
+  DecTiles R;
+  const int al = S->epilogue == QEFT_EPI_SWIGLU ? 2 : 1;     // SwiGLU: gate / up qweight rows alternate, CTAs own pairs
+  const unsigned Qa = (unsigned)(S->total_q / al);           // (total_q x grid < 2^31 is checked at program creation)
+  R.qa = al * (int)((Qa * (unsigned)cta) / (unsigned)ncta);
+  R.nq = al * (int)((Qa * (unsigned)(cta + 1)) / (unsigned)ncta) - R.qa;
+  R.ntiles = (R.nq + 3) >> 2;
+  return R;
+}
+
+// M: batch rows (1 or 2); the B fragment's 8 columns are M x 4 digit columns.
+//
+// Data path.  The CTA's work is a sequence of TILE-BLOCKS: 16 output rows (4 qweight rows) x up to kKB = 32 int4 steps
+// of 128 columns (32 KB), the last block of a tile also carrying the tile's fp16 outlier columns.  A ring of L.nslots
+// slots holds them; a slot is filled by
+//   * 4 bulk copies (one per qweight row, up to 8 KB each, TMA engine; destination rows staggered by 16 bytes),
+//   * cp.async copies of the block's scale / scaled-zero rows (8 bytes per qweight row and step) and outlier columns,
+// all completing on the slot's mbarrier.  All 16 warps consume a block together (warp w: steps w and w + 16, A fragments
+// by conflict-free ldmatrix straight from the copied bytes), and the LAST warp to finish a block refills its slot with
+// the block nslots ahead in the sequence -- which may belong to a later stage: the stream does not stop at a stage
+// boundary, ~150 KB per SM stay in flight while the CTAs meet at the barrier and convert the next x.
+template <int M>
+__global__ void __launch_bounds__(kDBlock, 1)
 decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, unsigned* sync, const DecLayout L) {
   extern __shared__ __align__(128) uint8_t dsm[];
   constexpr int NCOLS = 4 * M;
-  constexpr uint32_t XSTEP = 128u * NCOLS;                   // digit bytes per 128-column step: [2 halves][NCOLS][4 t][16 B]
+  constexpr uint32_t XSTEP = 128u * NCOLS;                   // digit bytes per 128-column step: [2 nibble halves][NCOLS][4 t][16 B]
   constexpr uint32_t XHALF = 64u * NCOLS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int cta = blockIdx.x, ncta = gridDim.x;
+  const int NS = L.nslots;
 
-  const uint32_t ring = d_smem_u32(dsm) + (uint32_t)(warp * D * kSlot);
-  const uint32_t ring_end = ring + D * kSlot;
+  const uint32_t ring = d_smem_u32(dsm);
   const uint32_t xdig = d_smem_u32(dsm + L.xdig);
   const uint32_t xsum = d_smem_u32(dsm + L.xsum);            // [nsteps][2] fp32 group sums of x
   const uint32_t xo = d_smem_u32(dsm + L.xo);                // [M][r] fp16 outlier activations
-  float* part = reinterpret_cast<float*>(dsm + L.part);      // [warp][touch][2 kinds][M][16 rows]
+  float* part = reinterpret_cast<float*>(dsm + L.part);      // [tile][warp][M][16 rows]
   float* red = reinterpret_cast<float*>(dsm + L.misc);       // [16 warps][4] staging reductions
   float* coef = red + kDWarps * 4;                           // [8] flush weights of a quad's accumulator columns
-  const int MT = L.max_touch;
+  const uint32_t bars = d_smem_u32(dsm + L.misc + 512);      // [nslots] "slot filled" mbarriers
+  const uint32_t ebars = bars + 64;                          // [nslots] "slot consumed" mbarriers (16 warp arrivals)
+  DecStage* pcache = reinterpret_cast<DecStage*>(dsm + L.misc + 768);     // descriptor of the producer's stage
+  DecStage* ccache = reinterpret_cast<DecStage*>(dsm + L.misc + 1280);    // descriptor of the stage being consumed
+  static_assert(sizeof(DecStage) <= 384 && sizeof(DecStage) % 4 == 0, "descriptor cache slots are 384 bytes");
+  constexpr int kStageWords = (int)(sizeof(DecStage) / 4);
 
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      d_mbar_init(bars + 8 * i, 1);                          // one arrive.expect_tx per fill; the bytes arrive by bulk copies
+      d_mbar_init(ebars + 8 * i, kDWarps);                   // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // (stage descriptors live in global memory; every fence of the stage barrier drops them from L1, and a chain of
+  // dependent L2 round trips per block is what made the first versions of this kernel slow: they are read from a
+  // shared-memory copy instead)
+  if (tid >= 32 && tid < 32 + kStageWords)
+    reinterpret_cast<uint32_t*>(ccache)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s_begin)[tid - 32];
   // the barrier counter only grows; `base` is its value when every CTA of this launch has started
   const unsigned base = *reinterpret_cast<volatile unsigned*>(sync + 1);
+  __syncthreads();
 
-  // ---- prefetch cursor: walks the units of this warp through ALL stages of the launch --------------------------
-  // A tile's units are issued in phases of identical copies (running pointers, one counter); `ld_event` sets up the
-  // next phase: the tile's outlier columns, the next tile, the next stage, or the idle state after the last stage.
-  int ls = s_begin - 1, lj = 0, lvn = 0, lrem = 0, lcnt = 0, lU = 1, lns = 0;
-  const uint8_t* pcur = reinterpret_cast<const uint8_t*>(stages);   // this lane's 16 bytes of row 2g of the unit (any valid address when idle)
-  const uint8_t* scur = pcur;        // lanes 0..7: 8 bytes of scales (lanes 0..3) / scaled zeros (4..7) of qweight row lane & 3
-  uint32_t poff2 = 0, pstride = 0, sinc = 0;   // row 2g+1 - row 2g; bytes per unit; bytes per scale group
-  int wign = 1, sign = 1, sact = 0;  // ignore-src (zero-fill) flags of rows not owned; lanes that copy scales
-  auto ld_phase = [&](int v) {
-    const DecStage* S = stages + ls;
-    const DecRun R = dec_run(S, cta, ncta, warp);
-    const int r = S->r;
-    const int qi = 4 * lj + (g >> 1);
-    const bool own = qi < R.nq;
-    int pi, lq;
-    dec_locate(S, R.qa + (own ? qi : 0), pi, lq);
-    const DecPart& P = S->part[pi];
-    wign = own ? 0 : 1;
-    int n;
-    if (v < lns) {
-      pcur = P.qw + (size_t)lq * (size_t)(2 * S->K) + (size_t)((t >> 1) * 128 + (g & 1) * 64 + (t & 1) * 16) + (size_t)v * 256;
-      poff2 = 32; pstride = 256;
-      n = lns - v;
-      sact = lane < 8;
-      const int qs = 4 * lj + (lane & 3);
-      const bool owns = qs < R.nq;
-      int pis, lqs;
-      dec_locate(S, R.qa + (owns ? qs : 0), pis, lqs);
-      const DecPart& Ps = S->part[pis];
-      const __half* sb = (((lane >> 2) & 1) ? Ps.szeros : Ps.scales) + 4 * lqs;
-      sign = owns ? 0 : 1;
-      const int g128 = S->g128;
-      const bool partial = (S->nchunks & 3) != 0;            // the last step has dead 32-column chunks
-      int grp;
-      if (g128 > 1) { n = 1; grp = v / g128; sinc = 0; }     // uncommon group sizes: one unit per phase
-      else {
-        grp = g128 == 1 ? v : 0;
-        sinc = g128 == 1 ? (uint32_t)(2 * Ps.N) : 0u;
-        if (partial && n > 1) n -= 1;                        // the last step is a phase of its own
-      }
-      if (partial && v == lns - 1 && 4 * v + t >= S->nchunks) wign = 1;
-      scur = reinterpret_cast<const uint8_t*>(sb + (size_t)grp * (size_t)Ps.N);
-    } else {
-      pcur = reinterpret_cast<const uint8_t*>(P.ow + ((size_t)(4 * lq + 2 * (g & 1)) * (size_t)r + (size_t)(8 * t + 32 * (v - lns))));
-      poff2 = (uint32_t)(2 * r); pstride = 64;
-      n = lU - v;
-      sact = 0; sinc = 0;
-    }
-    n = n < lrem ? n : lrem;
-    lcnt = n; lrem -= n; lvn = v + n;
-  };
-  auto ld_next_stage = [&]() {
-    for (;;) {
-      ++ls;
-      if (ls >= s_end) { lcnt = 0x7fffffff; wign = 1; sact = 0; pstride = 0; sinc = 0; poff2 = 0; return; }   // idle: zero-fills
-      const DecStage* S = stages + ls;
-      const DecRun R = dec_run(S, cta, ncta, warp);
-      if (R.u0 < R.u1) {
-        lU = R.U; lns = R.ns; lrem = R.u1 - R.u0;
-        lj = R.u0 / lU;
-        ld_phase(R.u0 - lj * lU);
-        return;
-      }
-    }
-  };
-  auto ld_issue = [&](uint32_t slot) {
-    const uint32_t mine = slot + lane * 16;
-    d_cp16z(mine, pcur, wign);
-    d_cp16z(mine + 512, pcur + poff2, wign);
-    d_cp8z_if(slot + kSlotScale + lane * 8, scur, sact, sign);
-    d_commit();                      // always one group per unit: the group count is the ring's clock
-    pcur += pstride; scur += sinc;
-    if (--lcnt == 0) {
-      if (lrem == 0) ld_next_stage();
-      else if (lvn == lU) { ++lj; ld_phase(0); }
-      else ld_phase(lvn);
-    }
-  };
+  // debug counters (QEFT_DECODE_STAMPS): warp 0 and warp 15 of CTA 0 and the producer warp, clock64 cycles
+  long long dbg_wait = 0, dbg_math = 0, dbg_issue = 0, dbg_fill = 0;
+  int dbg_nissue = 0, dbg_nwaited = 0, dbg_nblocks = 0;
+  const bool dbg = L.stamps != nullptr && cta == 0 && (warp == 0 || warp >= kDWarps - 1);
 
-  ld_next_stage();
+  // =================================== the producer warp ========================================================
+  // Walks the CTA's tile-blocks through ALL stages of the launch and fills the ring: it only ever waits for a slot to
+  // be consumed, never for the stage barrier, so the weight stream runs ahead across stage boundaries.
+  if (warp == kDWarps) {
+    int pslot = 0;
+    uint32_t ppar = 1;                                       // (first pass: "consumed" phases count as complete)
 #pragma unroll 1
-  for (int d = 0; d < D - 1; ++d) ld_issue(ring + d * kSlot);
+    for (int st = s_begin; st < s_end; ++st) {
+      __syncwarp();
+      for (int i = lane; i < kStageWords; i += 32)
+        reinterpret_cast<uint32_t*>(pcache)[i] = reinterpret_cast<const uint32_t*>(stages + st)[i];
+      __syncwarp();
+      const DecStage* S = pcache;
+      const DecTiles R = dec_tiles(S, cta, ncta);
+      const int K = S->K, r = S->r, ns = S->nsteps, g128 = S->g128;
+      const int KB = (ns + kKB - 1) / kKB;
+      const size_t row_bytes = (size_t)(2 * K);
+#pragma unroll 1
+      for (int j = 0; j < R.ntiles; ++j) {
+        // this lane's qweight row of the tile (lane & 3)
+        const int q = lane & 3, qi = 4 * j + q;
+        const bool own = qi < R.nq;
+        int pi, lq;
+        dec_locate(S, R.qa + (own ? qi : 0), pi, lq);
+        const DecPart& P = S->part[pi];
+        const unsigned own4 = __ballot_sync(0xffffffffu, own) & 0xfu;
+        const uint8_t* wsrc = P.qw + (size_t)lq * row_bytes;
+        const uint8_t* dsrc = P.side + (size_t)lq * (size_t)P.side_q;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          const long long t0 = dbg ? clock64() : 0;
+          const uint32_t sbase = ring + (uint32_t)pslot * (uint32_t)L.slot, bar = bars + 8 * pslot;
+          d_mbar_wait(ebars + 8 * pslot, ppar);              // all 16 warps are done with the slot's previous block
+          const int nsb = ns - kb * kKB < kKB ? ns - kb * kKB : kKB;
+          const size_t off = (size_t)kb * (size_t)(kKB * 256);
+          const uint32_t want = (uint32_t)(nsb * 256);
+          const uint32_t nbytes = (row_bytes - off) < want ? (uint32_t)(row_bytes - off) : want;   // (last step of a K % 128 == 64 row)
+          // side bytes of the block: its steps' scales / scaled zeros and, on the tile's last block, the outlier columns
+          // (they follow the last step's scales in the table, so it is one contiguous copy)
+          const uint32_t sbytes = (uint32_t)(nsb * 16 + (kb == KB - 1 ? 8 * r : 0));
+          if (lane == 0) d_mbar_expect_tx(bar, (uint32_t)__popc(own4) * (((L.debug & 4) ? 0u : nbytes) + ((L.debug & 2) ? 0u : sbytes)));
+          __syncwarp();
+          // rows this CTA does not own are NOT copied: their slot bytes are stale, their (independent) MMA rows are never stored
+          if (lane < 4 && own && !(L.debug & 4)) d_bulk_g2s(sbase + (uint32_t)(q * kQArea), wsrc + off, nbytes, bar);
+          if (lane < 4 && own && !(L.debug & 2))
+            d_bulk_g2s(sbase + (uint32_t)(L.slot_s + q * L.sarea), dsrc + (size_t)kb * (size_t)kSideSteps, sbytes, bar);
+          if (++pslot == NS) { pslot = 0; ppar ^= 1u; }
+          if (dbg) { dbg_issue += clock64() - t0; ++dbg_nissue; }
+        }
+      }
+    }
+    if (dbg && lane == 0) {
+      unsigned long long* o = L.stamps + (size_t)(s_end - s_begin) * 32 + 16;
+      o[0] = (unsigned long long)dbg_issue; o[1] = (unsigned long long)dbg_nissue;
+    }
+    return;
+  }
 
-  uint32_t slot = ring, prev_slot = ring + (D - 1) * kSlot;
-  const uint32_t xdig_lane = xdig + (uint32_t)(g * 64 + t * 16);
+  // =================================== the 16 consumer warps ====================================================
+  int cslot = 0;
+  uint32_t cpar = 0;
   const int has_col = g < NCOLS;
   // batch 1: lane t = 2 of every quad accumulates the zero-point term (its accumulator columns are no digits)
   const bool zlane = M == 1 && t == 2;
-  const uint32_t soff_lane = (uint32_t)(kSlotScale + 4 * g + (zlane ? 32 : 0));
   const int gx = g < M ? g : 0;
-
-  // one unit: wait for the oldest group, refill the slot read one unit ago, fetch this lane's 32 bytes
-#define QEFT_DEC_UNIT_BEGIN()                                   \
-  d_wait<D - 2>();                                              \
-  __syncwarp();                                                 \
-  ld_issue(prev_slot);                                          \
-  const uint32_t mine = slot + lane * 16;                       \
-  const uint4 va = d_lds128(mine), vb = d_lds128(mine + 512);
-#define QEFT_DEC_UNIT_END()                                     \
-  prev_slot = slot;                                             \
-  slot += kSlot;                                                \
-  if (slot == ring_end) slot = ring;
+  // ldmatrix row addresses: lane l supplies row (l & 7) of matrix (l >> 3): matrices 0 / 2 = tile rows 2 i (MMA rows 0..7),
+  // 1 / 3 = tile rows 2 i + 1 (MMA rows 8..15); matrices 2, 3 are the second 16-byte chunk
+  const int lrow = 2 * (lane & 7) + ((lane >> 3) & 1);
+  const uint32_t laneA = (uint32_t)((lrow >> 2) * kQArea + (lrow & 3) * 32 + (lane >> 4) * 16);
+  // side area of this lane's qweight row (g >> 1): per step 16 bytes {scales of its 4 rows | scaled zeros}; rows 2g, 2g+1
+  // are the pair (g & 1) of the row; the outlier fragments follow the block's last step
+  const uint32_t laneS = (uint32_t)(L.slot_s + (g >> 1) * L.sarea + (g & 1) * 4 + (zlane ? 8 : 0));
+  const uint32_t laneO = (uint32_t)(L.slot_s + (g >> 1) * L.sarea + (g & 1) * 64 + t * 16);
+  const uint32_t xdig_lane = xdig + (uint32_t)(g * 64 + t * 16);
 
 #pragma unroll 1
   for (int s = s_begin; s < s_end; ++s) {
-    const DecStage* S = stages + s;
-    const DecRun R = dec_run(S, cta, ncta, warp);
-    const int K = S->K, r = S->r, ns = S->nsteps;
+    const DecStage* S = ccache;              // (the copy of stage s; complete after the barrier below / the initial sync)
 
     if (s > s_begin) {
       // ---- stage boundary: every CTA has stored its rows of the previous stage -------------------------------
@@ -333,18 +395,39 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         if (cta == 0 && s == s_begin + 1)       // every CTA has read `base`: publish the next launch's base
           *reinterpret_cast<volatile unsigned*>(sync + 1) = base + (unsigned)(s_end - s_begin - 1) * (unsigned)ncta;
       }
-      __syncthreads();
+      d_consumer_sync();
     }
+    const DecTiles R = dec_tiles(S, cta, ncta);
+    const int K = S->K, r = S->r, ns = S->nsteps;
 
     dec_stamp(L, s, 0);
     // ---- x: four signed-byte digits of a 30-bit fixed point, one exponent per batch row ----------------------
     {
       const __half* xg = S->x;
+      // o_proj's gather (qlinear.py:275): copy x to shared memory first (coalesced, one L2 round trip; the buffer aliases
+      // the partial-sum slices, idle between two stages), then gather from there instead of 16 scattered 2-byte L2 loads
+      const bool xraw_ok = S->gather != nullptr && (size_t)M * (size_t)K * 2 <= (size_t)L.part_bytes;
+      const uint32_t xraw = d_smem_u32(dsm + L.part);
+      if (xraw_ok) {
+        for (int i = tid; i < M * (K >> 3); i += kDThreads) {
+          const uint4 v = d_ldcg128(xg + (size_t)i * 8);
+          d_sts128(xraw + (uint32_t)i * 16, v.x, v.y, v.z, v.w);
+        }
+        d_consumer_sync();
+      }
+      auto ldx16 = [&](const __half* row, int b, int col) -> unsigned short {
+        if (xraw_ok) {
+          unsigned short r16;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16) : "r"(xraw + (uint32_t)((b * K + col) * 2)) : "memory");
+          return r16;
+        }
+        return d_ldcg16(row + col);
+      };
       const int32_t* gat = S->gather;
       const __half* nw = S->norm_w;
       const int live_k = S->nchunks * 32;
       const int nitems = M * ns * 8;
-      constexpr int kKeep = 3;
+      constexpr int kKeep = 2;
       uint4 keep[kKeep][2];
       float mx0 = 0.f, mx1 = 0.f, ss0 = 0.f, ss1 = 0.f;
       // item = (batch row b, step, chunk tt, hs): the 16 columns k0 .. k0+7 and k0+16 .. k0+23, k0 = 128 step + 32 tt + 8 hs
@@ -360,7 +443,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           if (gat) {
             const int4 i0 = __ldg(reinterpret_cast<const int4*>(gat + k0)), i1 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 4));
             const int4 i2 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 16)), i3 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 20));
-            auto pk = [&](int a, int c) { return (uint32_t)d_ldcg16(xr + a) | ((uint32_t)d_ldcg16(xr + c) << 16); };
+            auto pk = [&](int a, int c) { return (uint32_t)ldx16(xr, b, a) | ((uint32_t)ldx16(xr, b, c) << 16); };
             v0 = make_uint4(pk(i0.x, i0.y), pk(i0.z, i0.w), pk(i1.x, i1.y), pk(i1.z, i1.w));
             v1 = make_uint4(pk(i2.x, i2.y), pk(i2.z, i2.w), pk(i3.x, i3.y), pk(i3.z, i3.w));
           } else {
@@ -432,7 +515,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         const __half* xr = xg + (size_t)b * K;
         if (gat) {
           const int4 a = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj)), c = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj + 4));
-          auto pk = [&](int i0, int i1) { return (uint32_t)d_ldcg16(xr + i0) | ((uint32_t)d_ldcg16(xr + i1) << 16); };
+          auto pk = [&](int i0, int i1) { return (uint32_t)ldx16(xr, b, i0) | ((uint32_t)ldx16(xr, b, i1) << 16); };
           xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
         } else {
           xo_v = d_ldcg128(xr + K - r + 8 * jj);
@@ -445,6 +528,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           if (b == 0) ss0 += ss; else ss1 += ss;
         }
       }
+      dec_stamp(L, s, 4);
       // CTA-wide maximum (and sum of squares) per batch row
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
@@ -459,7 +543,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         }
       }
       if (lane == 0) { red[warp * 4 + 0] = mx0; red[warp * 4 + 1] = mx1; red[warp * 4 + 2] = ss0; red[warp * 4 + 3] = ss1; }
-      __syncthreads();
+      d_consumer_sync();
       mx0 = mx1 = ss0 = ss1 = 0.f;
 #pragma unroll
       for (int w = 0; w < kDWarps; ++w) {
@@ -486,6 +570,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         if (M == 1 && tid == 4) c = 1.f;            // batch 1: lane t = 2 carries the zero-point sums unscaled
         coef[tid] = c;
       }
+      dec_stamp(L, s, 5);
       // pass B: digits
       for (int q = 0; q < npass; ++q) {
         const int it = q * kDThreads + tid;
@@ -540,20 +625,23 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           uint32_t dg[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { dg[2 * j] = digits(f[j].x); dg[2 * j + 1] = digits(f[j].y); }
-          // digit row d, word c: bytes {first[2c], second[2c], first[2c+1], second[2c+1]} (first = k0 + ., second = k0 + 16 + .)
-          const uint32_t dst = xdig + (uint32_t)(st * XSTEP + hs * XHALF + (4 * b) * 64 + tt * 16);
+          // Word c of digit column d = bytes {first[2c], second[2c], first[2c+1], second[2c+1]} (first = k0 + ., second =
+          // k0 + 16 + .): the B-fragment register of lane t = c for this item's 32-column chunk tt = 2 T + h and nibble
+          // position hs.  Lane t's 16-byte row of (hs, column) holds its four chunks' words, index tt.
+          const uint32_t dst = xdig + (uint32_t)st * XSTEP + (uint32_t)hs * XHALF + (uint32_t)(4 * b) * 64 + (uint32_t)tt * 4;
 #pragma unroll
           for (int d = 0; d < 4; ++d) {
             const uint32_t sel = 0x0040u + 0x11u * (uint32_t)d;
-            uint32_t ww[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              ww[c] = d_prmt(d_prmt(dg[2 * c], dg[8 + 2 * c], sel), d_prmt(dg[2 * c + 1], dg[8 + 2 * c + 1], sel), 0x5410u);
-            d_sts128(dst + d * 64, ww[0], ww[1], ww[2], ww[3]);
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t ww = d_prmt(d_prmt(dg[2 * c], dg[8 + 2 * c], sel), d_prmt(dg[2 * c + 1], dg[8 + 2 * c + 1], sel), 0x5410u);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + (uint32_t)(d * 64 + c * 16)), "r"(ww) : "memory");
+            }
           }
           if ((it & 7) == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + (uint32_t)(st * 8 + b * 4)), "f"(sum) : "memory");
         }
       }
+      dec_stamp(L, s, 6);
       if (xo_tid < nxo) {
         const int b = xo_tid / (r >> 3), jj = xo_tid - b * (r >> 3);
         if (nw) {
@@ -571,46 +659,59 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         }
         d_sts128(xo + (uint32_t)((b * r + 8 * jj) * 2), xo_v.x, xo_v.y, xo_v.z, xo_v.w);
       }
-      __syncthreads();
+      d_consumer_sync();
     }
 
     dec_stamp(L, s, 1);
-    // ---- this warp's units of the stage ------------------------------------------------------------------------
+    // ---- the tile-blocks of the stage -------------------------------------------------------------------------
     {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};    // rows 2g, 2g+1 x accumulator columns 2t, 2t+1: sum over groups of scale * P
-      float zacc0 = 0.f, zacc1 = 0.f;         // M = 2: rows 2g, 2g+1, sum over groups of scaled zero * X_g, batch row t >> 1
-      float yo[4] = {0.f, 0.f, 0.f, 0.f};     // outlier columns: rows 2g, 2g+1 x batch rows 2t, 2t+1
-      uint4 xe = make_uint4(0u, 0u, 0u, 0u), xq = xe;
-      const int U = R.U;
-      int v = R.u0 - (R.u0 / U) * U, rem = R.u1 - R.u0, touch = 0;
-      while (rem > 0) {
-        if (v < ns) {
-          int n = ns - v < rem ? ns - v : rem;
-          uint32_t xc = xdig_lane + (uint32_t)v * XSTEP;
-          uint32_t xsa = xsum + (uint32_t)(v * 8 + (M == 2 ? (t >> 1) * 4 : 0));
-          rem -= n; v += n;
+      const int KB = (ns + kKB - 1) / kKB;
+      const uint32_t xo_lane = xo + (uint32_t)((gx * r + 2 * t) * 2);
+      uint4 xe = make_uint4(0u, 0u, 0u, 0u), xq = xe, xe2 = xe, xq2 = xe;
 #pragma unroll 1
-          for (; n > 0; --n) {
-            // one 128-column int4 step of 16 rows: two AND masks per word (low nibbles q, high nibbles 16 q: both valid
-            // u8), 4 IMMA with exact s32 accumulation; 16 lo + hi = 16 sum(q X)
-            QEFT_DEC_UNIT_BEGIN();
-            d_lds128_if(xe, xc, has_col);
-            d_lds128_if(xq, xc + XHALF, has_col);
-            const uint32_t sw = d_lds32(slot + soff_lane);
-            const float xs = d_ldsf(xsa);
+      for (int j = 0; j < R.ntiles; ++j) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};    // rows 2g, 2g+1 x accumulator columns 2t, 2t+1: sum over groups of scale * P
+        float zacc0 = 0.f, zacc1 = 0.f;         // M = 2: rows 2g, 2g+1, sum over groups of scaled zero * X_g, batch row t >> 1
+        float yo[4] = {0.f, 0.f, 0.f, 0.f};     // outlier columns: rows 2g, 2g+1 x batch rows 2t, 2t+1
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t sbase = ring + (uint32_t)cslot * (uint32_t)L.slot;
+          // wait for the block (lane 0 polls, so that the loop is warp-uniform); meanwhile help refilling free slots
+          const long long tw0 = dbg ? clock64() : 0;
+          const bool ready0 = d_mbar_test(bars + 8 * cslot, cpar);
+          d_mbar_wait(bars + 8 * cslot, cpar);               // the block's bytes have landed (every lane acquires them)
+          const long long tw1 = dbg ? clock64() : 0;
+          if (dbg) { dbg_wait += tw1 - tw0; ++dbg_nblocks; if (!ready0) ++dbg_nwaited; }
+          const int nsb = ns - kb * kKB < kKB ? ns - kb * kKB : kKB;
+          // one 128-column int4 step of 16 rows: A fragments by ldmatrix from the copied bytes, two AND masks per word
+          // (low nibbles q, high nibbles 16 q: both valid u8), 4 IMMA with exact s32 accumulation; 16 lo + hi = 16 sum(q X).
+          // A warp's two steps of the block (warp, warp + 16) are loaded together and then computed: twice the loads
+          // in flight per warp.
+          auto load_step = [&](int st, uint32_t (&a0)[4], uint32_t (&a1)[4], uint4& xe_, uint4& xq_, uint32_t& sw, uint32_t& zw, float& xs) {
+            const int gs = kb * kKB + st;
+            d_ldmatrix_x4(a0, sbase + laneA + (uint32_t)(st * 256));
+            d_ldmatrix_x4(a1, sbase + laneA + (uint32_t)(st * 256 + 128));
+            const uint32_t xc = xdig_lane + (uint32_t)gs * XSTEP;
+            d_lds128_if(xe_, xc, has_col);
+            d_lds128_if(xq_, xc + XHALF, has_col);
+            sw = d_lds32(sbase + laneS + (uint32_t)(st * 16));
+            zw = M == 2 ? d_lds32(sbase + laneS + (uint32_t)(st * 16 + 8)) : 0u;
+            xs = d_ldsf(xsum + (uint32_t)(gs * 8 + (M == 2 ? (t >> 1) * 4 : 0)));
+          };
+          auto math_step = [&](const uint32_t (&a0)[4], const uint32_t (&a1)[4], const uint4& xe_, const uint4& xq_, uint32_t sw, uint32_t zw, float xs) {
             constexpr uint32_t kLoM = 0x0f0f0f0fu, kHiM = 0xf0f0f0f0u;
             int lo[4], hi[4];
-            d_imma0(lo, va.x & kLoM, vb.x & kLoM, va.y & kLoM, vb.y & kLoM, xe.x, xe.y);
-            d_imma0(hi, va.x & kHiM, vb.x & kHiM, va.y & kHiM, vb.y & kHiM, xq.x, xq.y);
-            d_imma(lo, va.z & kLoM, vb.z & kLoM, va.w & kLoM, vb.w & kLoM, xe.z, xe.w);
-            d_imma(hi, va.z & kHiM, vb.z & kHiM, va.w & kHiM, vb.w & kHiM, xq.z, xq.w);
+            d_imma0(lo, a0[0] & kLoM, a0[1] & kLoM, a0[2] & kLoM, a0[3] & kLoM, xe_.x, xe_.y);
+            d_imma0(hi, a0[0] & kHiM, a0[1] & kHiM, a0[2] & kHiM, a0[3] & kHiM, xq_.x, xq_.y);
+            d_imma(lo, a1[0] & kLoM, a1[1] & kLoM, a1[2] & kLoM, a1[3] & kLoM, xe_.z, xe_.w);
+            d_imma(hi, a1[0] & kHiM, a1[1] & kHiM, a1[2] & kHiM, a1[3] & kHiM, xq_.z, xq_.w);
             const float2 sc = half2_bits_to_float2(sw);
             float f0 = (float)(lo[0] * 16 + hi[0]), f2 = (float)(lo[2] * 16 + hi[2]);
             const float f1 = (float)(lo[1] * 16 + hi[1]), f3 = (float)(lo[3] * 16 + hi[3]);
             if (M == 1) {
               if (zlane) { f0 = xs; f2 = xs; }               // scaled zero x group sum of x in the zero-point lane
             } else {
-              const float2 zz = half2_bits_to_float2(d_lds32(slot + kSlotScale + 32 + 4 * g));
+              const float2 zz = half2_bits_to_float2(zw);
               zacc0 = fmaf(zz.x, xs, zacc0);
               zacc1 = fmaf(zz.y, xs, zacc1);
             }
@@ -618,61 +719,57 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             acc[1] = fmaf(sc.x, f1, acc[1]);
             acc[2] = fmaf(sc.y, f2, acc[2]);
             acc[3] = fmaf(sc.y, f3, acc[3]);
-            xc += XSTEP; xsa += 8;
-            QEFT_DEC_UNIT_END();
+          };
+          if (warp < nsb && !(L.debug & 1)) {
+            uint32_t a0[4], a1[4], b0[4], b1[4], sw0, sw1 = 0, zw0, zw1 = 0;
+            float xs0, xs1 = 0.f;
+            const bool two = warp + kDWarps < nsb;
+            load_step(warp, a0, a1, xe, xq, sw0, zw0, xs0);
+            if (two) load_step(warp + kDWarps, b0, b1, xe2, xq2, sw1, zw1, xs1);
+            math_step(a0, a1, xe, xq, sw0, zw0, xs0);
+            if (two) math_step(b0, b1, xe2, xq2, sw1, zw1, xs1);
           }
-        }
-        if (rem > 0 && v < U) {
-          int n = U - v < rem ? U - v : rem;
-          uint32_t xoa = xo + (uint32_t)((gx * r + 8 * t + 32 * (v - ns)) * 2);
-          rem -= n; v += n;
+          if (kb == KB - 1 && r > 0 && !(L.debug & 1)) {
+            // 16 fp16 outlier columns of 16 rows per unit: one HMMA; units go to the warps from the top
 #pragma unroll 1
-          for (; n > 0; --n) {
-            // 32 fp16 outlier columns of 16 rows: 2 HMMA
-            QEFT_DEC_UNIT_BEGIN();
-            const uint4 xv = d_lds128(xoa);
-            mma_m16n8k16_f16f32(yo, va.x, vb.x, va.y, vb.y, xv.x, xv.y);
-            mma_m16n8k16_f16f32(yo, va.z, vb.z, va.w, vb.w, xv.z, xv.w);
-            xoa += 64;
-            QEFT_DEC_UNIT_END();
+            for (int u = kDWarps - 1 - warp; u < (r >> 4); u += kDWarps) {
+              const uint4 a4 = d_lds128(sbase + laneO + (uint32_t)(nsb * 16 + u * 128));
+              const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+              const uint32_t b0 = d_lds32(xo_lane + (uint32_t)(u * 32)), b1 = d_lds32(xo_lane + (uint32_t)(u * 32 + 16));
+              mma_m16n8k16_f16f32(yo, a[0], a[1], a[2], a[3], b0, b1);
+            }
           }
+          // this warp is done with the slot
+          __syncwarp();
+          if (dbg) dbg_math += clock64() - tw1;
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ebars + 8 * cslot) : "memory");
+          if (++cslot == NS) { cslot = 0; cpar ^= 1u; }
         }
         {
-          // end of this warp's share of the tile: accumulator columns -> one value per (row, batch row), to this warp's slice
+          // end of the tile: accumulator columns -> one value per (row, batch row), to this warp's slice of the tile
           const float c0 = coef[2 * t], c1 = coef[2 * t + 1];
           float v1 = fmaf(c0, acc[0], c1 * acc[1]), v2 = fmaf(c0, acc[2], c1 * acc[3]);
           v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
           v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+          float* dst = part + (size_t)((j * kDWarps + warp) * M) * 16;
           if (M == 1) {
             v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
             v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+            if (t == 0) { dst[2 * g] = v1 + yo[0]; dst[2 * g + 1] = v2 + yo[2]; }
+          } else {
+            // batch row 1's outlier sums live in lane t = 0 of the quad (accumulator column 1)
+            const float o1 = __shfl_sync(0xffffffffu, yo[1], lane & ~3), o3 = __shfl_sync(0xffffffffu, yo[3], lane & ~3);
+            if (t == 0) { dst[2 * g] = v1 + zacc0 + yo[0]; dst[2 * g + 1] = v2 + zacc1 + yo[2]; }
+            if (t == 2) { dst[16 + 2 * g] = v1 + zacc0 + o1; dst[16 + 2 * g + 1] = v2 + zacc1 + o3; }
           }
-          float* dst = part + ((size_t)(warp * MT + touch) * 2) * (size_t)(M * 16);
-          if (M == 1) {
-            if (t == 0) { dst[2 * g] = v1; dst[2 * g + 1] = v2; }
-          } else if ((t & 1) == 0) {
-            dst[(t >> 1) * 16 + 2 * g] = v1 + zacc0;
-            dst[(t >> 1) * 16 + 2 * g + 1] = v2 + zacc1;
-          }
-          if (t == 0) {
-            float* dso = dst + M * 16;
-            dso[2 * g] = yo[0]; dso[2 * g + 1] = yo[2];
-            if (M > 1) { dso[16 + 2 * g] = yo[1]; dso[16 + 2 * g + 1] = yo[3]; }
-          }
-          acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-          zacc0 = zacc1 = 0.f;
-          yo[0] = yo[1] = yo[2] = yo[3] = 0.f;
-          ++touch;
-          if (v == U) v = 0;
         }
       }
     }
-    __syncthreads();
+    d_consumer_sync();
     dec_stamp(L, s, 2);
 
     // ---- add the warps' slices in a fixed order, epilogue, store the rows this CTA owns -------------------------
     {
-      const int U = R.U, TU = R.ntiles * U;
       const int epi = S->epilogue;
       const int nitems = R.ntiles * 16 * M;
       for (int i = tid; i < nitems; i += kDThreads) {
@@ -681,15 +778,10 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         if (qi >= R.nq) continue;
         if (epi == QEFT_EPI_SWIGLU && (rr & 4)) continue;          // up rows are consumed by their gate rows
         auto tile_sum = [&](int row) {
+          const float* src = part + (size_t)(j * kDWarps * M + b) * 16 + row;
           float a = 0.f;
-#pragma unroll 1
-          for (int w = 0; w < kDWarps; ++w) {
-            const int w0 = (w * TU) / kDWarps, w1 = ((w + 1) * TU) / kDWarps;
-            if (w0 < w1 && w0 < (j + 1) * U && w1 > j * U) {      // the warp's (non-empty) run overlaps tile j
-              const float* src = part + ((size_t)(w * MT + (j - w0 / U)) * 2) * (size_t)(M * 16);
-              a += src[b * 16 + row] + src[M * 16 + b * 16 + row];
-            }
-          }
+#pragma unroll
+          for (int w = 0; w < kDWarps; ++w) a += src[w * M * 16];
           return a;
         };
         int pi, lq;
@@ -715,21 +807,28 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       }
     }
     if (s + 1 < s_end) {
-      __syncthreads();
+      d_consumer_sync();
       if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
+      // the next stage's descriptor (read only after the barrier's __syncthreads)
+      if (tid >= 32 && tid < 32 + kStageWords)
+        reinterpret_cast<uint32_t*>(ccache)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s + 1)[tid - 32];
     }
     dec_stamp(L, s, 3);
   }
-  d_wait<0>();
+  if (dbg && lane == 0) {
+    unsigned long long* o = L.stamps + (size_t)(s_end - s_begin) * 32 + (warp == 0 ? 0 : 8);
+    o[0] = (unsigned long long)dbg_wait; o[1] = (unsigned long long)dbg_math; o[2] = 0;
+    o[3] = (unsigned long long)dbg_fill; o[4] = 0; o[5] = (unsigned long long)dbg_nwaited;
+    o[6] = (unsigned long long)dbg_nblocks; o[7] = (unsigned long long)clock64();
+  }
 }
-#undef QEFT_DEC_UNIT_BEGIN
-#undef QEFT_DEC_UNIT_END
 
 // ----------------------------------------------------------------------------------------------------
 struct DecProgram {
   DecStage* d_stages = nullptr;
   unsigned* d_sync = nullptr;
   unsigned long long* d_stamps = nullptr;
+  std::vector<void*> side_tables;
   std::vector<DecStage> h_stages;
   int m = 1;
   int device = 0;
@@ -741,9 +840,9 @@ static int dec_env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int D, int M>
+template <int M>
 static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, size_t smem, int grid, cudaStream_t stream) {
-  auto kern = decode_w4_kernel<D, M>;
+  auto kern = decode_w4_kernel<M>;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -754,7 +853,7 @@ static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, s
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kDThreads);
+  cfg.blockDim = dim3(kDBlock);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -812,10 +911,13 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
       dp.ow = r > 0 ? static_cast<const __half*>(a.oweight) : static_cast<const __half*>(a.scales);
       dp.bias = static_cast<const __half*>(a.bias);
       dp.y = static_cast<__half*>(a.y);
+      dp.side = nullptr;
+      dp.side_q = cdiv(K - r, 128) * 16 + 8 * r;
       dp.N = a.N;
       dp.q_begin = total_q;
       total_q += a.N / 4;
     }
+    if (st == QEFT_OK && (long)total_q * 1024 >= (1L << 31)) st = QEFT_E_UNSUPPORTED;   // 32-bit row arithmetic in the kernel
     if (st != QEFT_OK) { delete p; return st; }
     d.x = static_cast<const __half*>(q.x);
     d.gather = q.x_gather;
@@ -831,6 +933,32 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
     d.total_q = total_q;
     d.epilogue = q.epilogue;
   }
+  // the decode side tables (see dec_build_side_kernel): one per projection, owned by the program
+  for (int s = 0; s < nstages; ++s) {
+    DecStage& d = p->h_stages[s];
+    for (int i = 0; i < d.nparts; ++i) {
+      DecPart& dp = d.part[i];
+      void* buf = nullptr;
+      cudaError_t e = cudaMalloc(&buf, (size_t)(dp.N / 4) * (size_t)dp.side_q);
+      if (e != cudaSuccess) {
+        for (void* b : p->side_tables) cudaFree(b);
+        delete p;
+        return (int)e;
+      }
+      p->side_tables.push_back(buf);
+      dec_build_side_kernel<<<dp.N / 4, 128>>>(dp.scales, dp.szeros, dp.ow, static_cast<uint8_t*>(buf), dp.N, d.r, d.g128, d.nsteps, dp.side_q);
+      dp.side = static_cast<const uint8_t*>(buf);
+    }
+  }
+  {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      for (void* b : p->side_tables) cudaFree(b);
+      delete p;
+      return (int)e;
+    }
+  }
   cudaGetDevice(&p->device);
   if (cudaDeviceGetAttribute(&p->nsm, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess || p->nsm <= 0) p->nsm = 148;
   cudaError_t e = cudaMalloc(&p->d_stages, sizeof(DecStage) * (size_t)nstages);
@@ -840,6 +968,7 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
   if (e != cudaSuccess) {
     if (p->d_stages) cudaFree(p->d_stages);
     if (p->d_sync) cudaFree(p->d_sync);
+    for (void* b : p->side_tables) cudaFree(b);
     delete p;
     return (int)e;
   }
@@ -853,6 +982,7 @@ extern "C" int qeft_decode_program_destroy(qeft_decode_program_t* prog) {
   cudaFree(p->d_stages);
   cudaFree(p->d_sync);
   if (p->d_stamps) cudaFree(p->d_stamps);
+  for (void* b : p->side_tables) cudaFree(b);
   delete p;
   return QEFT_OK;
 }
@@ -862,7 +992,7 @@ extern "C" __attribute__((visibility("default"))) int qeft_decode_debug_stamps(q
   if (!prog || !host_out) return QEFT_E_NULL;
   DecProgram* p = reinterpret_cast<DecProgram*>(prog);
   if (!p->d_stamps) return QEFT_E_UNSUPPORTED;
-  cudaError_t e = cudaMemcpy(host_out, p->d_stamps, p->h_stages.size() * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(host_out, p->d_stamps, (p->h_stages.size() * 32 + 24) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   return e == cudaSuccess ? QEFT_OK : (int)e;
 }
 
@@ -878,59 +1008,52 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   const int n = (int)p->h_stages.size();
   if (stage_begin < 0 || stage_end > n || stage_begin >= stage_end) return QEFT_E_SHAPE;
   static const int grid_env = dec_env_int("QEFT_DECODE_GRID", 0);
-  static const int depth_env = dec_env_int("QEFT_DECODE_DEPTH", 0);
+  static const int slots_env = dec_env_int("QEFT_DECODE_SLOTS", 0);
   const int grid = grid_env > 0 ? grid_env : p->nsm;
   const int m = p->m;
   // shared memory: the largest stage of the range sizes the x buffers and the partial-sum slices
-  int max_steps = 0, max_r = 0, max_touch = 1;
+  int max_steps = 0, max_r = 0, max_tiles = 1;
   for (int s = stage_begin; s < stage_end; ++s) {
     const DecStage& d = p->h_stages[s];
     max_steps = d.nsteps > max_steps ? d.nsteps : max_steps;
     max_r = d.r > max_r ? d.r : max_r;
     const int al = d.epilogue == QEFT_EPI_SWIGLU ? 2 : 1;
     const int nq_max = al * cdiv(d.total_q / al, grid);
-    const int T = cdiv(nq_max, 4), U = d.nsteps + d.nou;
-    const int run = cdiv(T * U, kDWarps);
-    const int touch = (run + U - 2) / U + 1;     // a run of `run` units starting anywhere in a tile
-    max_touch = touch > max_touch ? touch : max_touch;
+    const int T = cdiv(nq_max, 4);
+    max_tiles = T > max_tiles ? T : max_tiles;
   }
   DecLayout L;
-  size_t off = 0;   // the ring comes first; its size is decided below
+  L.slot_s = kSlotW;
+  L.sarea = kSideSteps + 8 * max_r;
+  L.slot = (int)(((size_t)(kSlotW + 4 * L.sarea) + 127) & ~(size_t)127);
   const size_t xdig = (size_t)max_steps * 128 * 4 * m;
   const size_t xsum = (size_t)max_steps * 8 + 16;
   const size_t xo = (size_t)m * max_r * 2 + 16;
-  const size_t part = (size_t)kDWarps * max_touch * 2 * m * 16 * sizeof(float);
-  const size_t misc = 1024;
+  const size_t part = (size_t)max_tiles * kDWarps * m * 16 * sizeof(float);
+  const size_t misc = 2048;
   const size_t fixed = ((xdig + 127) & ~(size_t)127) + ((xsum + 127) & ~(size_t)127) + ((xo + 127) & ~(size_t)127) +
                        ((part + 127) & ~(size_t)127) + misc;
-  if (fixed + (size_t)kDWarps * 3 * kSlot > kDSmemMax) return QEFT_E_UNSUPPORTED;
-  int depth = (int)((kDSmemMax - fixed) / ((size_t)kDWarps * kSlot));
-  if (depth_env > 0 && depth > depth_env) depth = depth_env;
-  depth = depth >= 10 ? 10 : (depth >= 8 ? 8 : (depth >= 6 ? 6 : (depth >= 4 ? 4 : 3)));
-  off = (size_t)kDWarps * depth * kSlot;
-  off = (off + 127) & ~(size_t)127;
+  if (fixed + 2 * (size_t)L.slot > kDSmemMax) return QEFT_E_UNSUPPORTED;
+  int nslots = (int)((kDSmemMax - fixed) / (size_t)L.slot);
+  if (nslots > 6) nslots = 6;
+  if (slots_env > 0 && nslots > slots_env) nslots = slots_env;
+  L.nslots = nslots;
+  size_t off = (size_t)nslots * (size_t)L.slot;
   L.xdig = (int)off; off += (xdig + 127) & ~(size_t)127;
   L.xsum = (int)off; off += (xsum + 127) & ~(size_t)127;
   L.xo = (int)off; off += (xo + 127) & ~(size_t)127;
   L.part = (int)off; off += (part + 127) & ~(size_t)127;
+  L.part_bytes = (int)part;
   L.misc = (int)off; off += misc;
-  L.max_touch = max_touch;
+  static const int debug_env = dec_env_int("QEFT_DECODE_DEBUG", 0);
+  L.debug = debug_env;
   static const int stamps_env = dec_env_int("QEFT_DECODE_STAMPS", 0);
   if (stamps_env && !p->d_stamps) {
-    const size_t bytes = (size_t)n * 16 * sizeof(unsigned long long);
+    const size_t bytes = ((size_t)n * 32 + 24) * sizeof(unsigned long long);
     if (cudaMalloc(&p->d_stamps, bytes) == cudaSuccess) cudaMemset(p->d_stamps, 0, bytes);
     else p->d_stamps = nullptr;
   }
   L.stamps = p->d_stamps;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define QEFT_DEC_LAUNCH(DD) \
-  (m == 1 ? dec_launch<DD, 1>(p, stage_begin, stage_end, L, off, grid, st) : dec_launch<DD, 2>(p, stage_begin, stage_end, L, off, grid, st))
-  switch (depth) {
-    case 10: return QEFT_DEC_LAUNCH(10);
-    case 8: return QEFT_DEC_LAUNCH(8);
-    case 6: return QEFT_DEC_LAUNCH(6);
-    case 4: return QEFT_DEC_LAUNCH(4);
-    default: return QEFT_DEC_LAUNCH(3);
-  }
-#undef QEFT_DEC_LAUNCH
+return m == 1 ? dec_launch<1>(p, stage_begin, stage_end, L, off, grid, st) : dec_launch<2>(p, stage_begin, stage_end, L, off, grid, st);
 }

@@ -25,7 +25,7 @@ def rel_err(got, want):
     return float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-6))
 
 
-def assert_close(got, want, what=""):
+def assert_close(got, want, what="", atol_rms=2e-3):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, (got.shape, want.shape)
@@ -33,7 +33,7 @@ def assert_close(got, want, what=""):
     e = rel_err(got, want)
     assert e <= REL_TOL, (what, e)
     rms = float(np.sqrt(np.mean(want ** 2))) + 1e-12
-    bad = np.abs(got - want) > 1e-3 * np.abs(want) + 2e-3 * rms
+    bad = np.abs(got - want) > 1e-3 * np.abs(want) + atol_rms * rms
     assert not bad.any(), (what, int(bad.sum()), float(np.max(np.abs(got - want)) / rms))
 
 
@@ -264,7 +264,9 @@ def test_swiglu_and_residual_epilogues(m):
     up = ref_forward(Lu, x)
     act = ((gate / (1 + np.exp(-gate))).astype(np.float16) * up).astype(np.float16)
     got_act = ys1[0].cpu().numpy()
-    assert_close(got_act, act, "swiglu")
+    # a product of two rounded projections: |d(silu(g) u)| <= |u| |dg| + |silu(g)| |du| with |u|, |g| up to ~4 rms, so
+    # the weight-rounding term of the elementwise bound is ~5x the single-projection one
+    assert_close(got_act, act, "swiglu", atol_rms=1.5e-2)
     want = (res.astype(np.float32) + ref_forward(Ld, got_act).astype(np.float32)).astype(np.float16)
     assert_close(ys2[0].cpu().numpy(), want, "residual")
 
@@ -309,3 +311,42 @@ def test_program_argument_errors():
     bad = dict(st, epilogue="swiglu")
     with pytest.raises(RuntimeError):
         qeft_cuda.DecodeProgram([bad])                     # needs exactly {gate, up}
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_fused_decoder_block_minus_attention(m):
+    """A Llama decoder block's linears AND the elementwise glue around them as four stages of one launch (SURVEY.md
+    8f3): [input RMSNorm -> q|k|v], [o_proj (reorder gather) + residual], [post-attention RMSNorm -> gate|up -> SiLU*mul],
+    [down_proj + residual].  Attention itself sits between stage 1 and 2 in a real decoder; here its output is a given
+    tensor.  Reference: HF LlamaDecoderLayer arithmetic on the oracle's projections, every intermediate rounded to fp16
+    where the unfused modules round."""
+    from qeft_b200 import qeft_cuda
+    h, f, r, eps = 512, 1408, 128, 1e-5
+    rng = np.random.default_rng(31 + m)
+    names = [("q", h, h), ("k", 256, h), ("v", 256, h), ("o", h, h), ("gate", f, h), ("up", f, h), ("down", h, f)]
+    Ls = {n: oracle.synth_layer(N, K, r=r, seed=300 + i, o_proj=(n == "o")) for i, (n, N, K) in enumerate(names)}
+    ids = oracle.sparse_to_dense_ids(Ls["o"]["outlieridx"], h)
+    hid = rng.standard_normal((m, h)).astype(np.float16)
+    attn = rng.standard_normal((m, h)).astype(np.float16)           # stand-in for the attention output
+    w1 = (1 + 0.1 * rng.standard_normal(h)).astype(np.float16)
+    w2 = (1 + 0.1 * rng.standard_normal(h)).astype(np.float16)
+    hid_d, attn_d = dev(hid), dev(attn)
+    s0, y_qkv = make_stage([Ls["q"], Ls["k"], Ls["v"]], hid_d, m, norm_weight=dev(w1), norm_eps=eps)
+    s1, y_h2 = make_stage([Ls["o"]], attn_d, m, x_gather=dev(ids.astype(np.int32)), epilogue="residual", residual=hid_d)
+    s2, y_act = make_stage([Ls["gate"], Ls["up"]], y_h2[0], m, norm_weight=dev(w2), norm_eps=eps, epilogue="swiglu")
+    s3, y_out = make_stage([Ls["down"]], y_act[0], m, epilogue="residual", residual=y_h2[0])
+    qeft_cuda.DecodeProgram([s0, s1, s2, s3], m=m).run()
+    torch.cuda.synchronize()
+    xn = _rmsnorm_ref(hid, w1, eps)
+    for n, y in zip(("q", "k", "v"), y_qkv):
+        assert_close(y.cpu().numpy(), ref_forward(Ls[n], xn), n)
+    h2 = (hid.astype(np.float32) + ref_forward(Ls["o"], attn, ids).astype(np.float32)).astype(np.float16)
+    got_h2 = y_h2[0].cpu().numpy()
+    assert_close(got_h2, h2, "h + o_proj(attn)")
+    xn2 = _rmsnorm_ref(got_h2, w2, eps)                              # from the device's own h2: the next stage read these bits
+    gate = ref_forward(Ls["gate"], xn2).astype(np.float32)
+    act = ((gate / (1 + np.exp(-gate))).astype(np.float16) * ref_forward(Ls["up"], xn2)).astype(np.float16)
+    got_act = y_act[0].cpu().numpy()
+    assert_close(got_act, act, "swiglu", atol_rms=1.5e-2)
+    out = (got_h2.astype(np.float32) + ref_forward(Ls["down"], got_act).astype(np.float32)).astype(np.float16)
+    assert_close(y_out[0].cpu().numpy(), out, "h2 + down_proj(act)")

@@ -24,17 +24,19 @@ def main():
         st.step_eager()
     torch.cuda.synchronize()
     n = prog.nstages
-    buf = np.zeros((n, 4, 4), dtype=np.uint64)
+    buf = np.zeros((n * 32 + 24,), dtype=np.uint64)
     lib = _lib.load()
     lib.qeft_decode_debug_stamps.restype = C.c_int
     lib.qeft_decode_debug_stamps.argtypes = [C.c_void_p, C.c_void_p]
     rc = lib.qeft_decode_debug_stamps(prog._h, buf.ctypes.data)
     assert rc == 0, rc
-    t = buf.astype(np.int64)
+    extra = buf[n * 32:].astype(np.int64)
+    t = buf[:n * 32].reshape(n, 4, 8).astype(np.int64)
     t0 = t[0, :, 0].min()
     rel = (t - t0) / 1e3     # us
     names = ["qkv", "o", "gateup", "down"]
-    agg = {k: {"wait": [], "stage_x": [], "consume": [], "reduce_store": []} for k in names}
+    agg = {k: {"wait": [], "stage_x": [], "consume": [], "reduce_store": [], "x_loads_max": [], "x_reduce": [],
+               "x_digits": [], "x_tail": []} for k in names}
     for s in range(1, n):
         k = names[s % 4]
         for c in range(4):
@@ -42,9 +44,19 @@ def main():
             agg[k]["stage_x"].append(rel[s, c, 1] - rel[s, c, 0])
             agg[k]["consume"].append(rel[s, c, 2] - rel[s, c, 1])
             agg[k]["reduce_store"].append(rel[s, c, 3] - rel[s, c, 2])
+            agg[k]["x_loads_max"].append(rel[s, c, 4] - rel[s, c, 0])
+            agg[k]["x_reduce"].append(rel[s, c, 5] - rel[s, c, 4])
+            agg[k]["x_digits"].append(rel[s, c, 6] - rel[s, c, 5])
+            agg[k]["x_tail"].append(rel[s, c, 1] - rel[s, c, 6])
     out = {k: {kk: round(float(np.median(vv)), 2) for kk, vv in v.items()} for k, v in agg.items()}
     out["total_us"] = round(float(rel[n - 1, :, 3].max()), 1)
-    out["first_stages_cta0_us"] = [[round(float(x), 2) for x in rel[s, 0]] for s in range(min(n, 8))]
+    out["first_stages_cta0_us"] = [[round(float(x), 2) for x in rel[s, 0, :4]] for s in range(min(n, 8))]
+    out["cta0_producer"] = {"issue_cycles": int(extra[16]), "issues": int(extra[17]),
+                            "cycles_per_block": round(float(extra[16]) / max(1, int(extra[17])), 1)}
+    for nm, e in (("warp0", extra[:8]), ("warp15", extra[8:16])):
+        out["cta0_" + nm] = {"wait_cycles": int(e[0]), "math_cycles": int(e[1]), "issue_cycles": int(e[2]),
+                             "fill_latency_cycles_when_waited": int(e[3]), "issues": int(e[4]), "blocks_waited": int(e[5]),
+                             "blocks": int(e[6])}
     print(json.dumps(out))
 
 
