@@ -106,7 +106,7 @@ struct DecStage {
 struct DecLayout {            // shared-memory carve-up (bytes from the start of dynamic shared memory)
   int nslots, slot;           // ring at offset 0: nslots slots of `slot` bytes: [4 x kQArea packed words][4 x sarea side bytes]
   int slot_s, sarea;
-  int xdig, xsum, xo, part, part_bytes, misc;
+  int xdig, xdig_bytes, xsum, xo, part, part_bytes, misc;
   int debug;                  // QEFT_DECODE_DEBUG bit mask (bisecting switches; results are WRONG when set)
   unsigned long long* stamps; // debug (QEFT_DECODE_STAMPS): [stage][4 CTAs][8] globaltimer values, or null
 };
@@ -300,6 +300,10 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const unsigned base = *reinterpret_cast<volatile unsigned*>(sync + 1);
   __syncthreads();
 
+  // the fourth digit column of every batch row is never written: it must read as zero (its accumulator column is unused)
+  for (int i = tid; i < L.xdig_bytes / 16; i += kDBlock) d_sts128(xdig + (uint32_t)i * 16, 0u, 0u, 0u, 0u);
+  __syncthreads();
+
   // debug counters (QEFT_DECODE_STAMPS): warp 0 and warp 15 of CTA 0 and the producer warp, clock64 cycles
   long long dbg_wait = 0, dbg_math = 0, dbg_issue = 0, dbg_fill = 0;
   int dbg_nissue = 0, dbg_nwaited = 0, dbg_nblocks = 0;
@@ -401,7 +405,11 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     const int K = S->K, r = S->r, ns = S->nsteps;
 
     dec_stamp(L, s, 0);
-    // ---- x: four signed-byte digits of a 30-bit fixed point, one exponent per batch row ----------------------
+    // ---- x: block fixed point per 128-column step, three signed-byte digits ------------------------------------------
+    //   x_k ~= X_k 2^(e-22),  X_k = d0 + 256 d1 + 65536 d2,  d_i in [-128, 127],  2^e > max |x| of the step
+    // (exact for every element within 12 binades of the step's maximum; fp16 has 11 significant bits).  One exponent per
+    // STEP keeps the staging free of a CTA-wide reduction (the stage boundary's critical path: measured 0.8 us for the
+    // first version's single exponent per row); the price is one multiply per row pair and step in the main loop.
     {
       const __half* xg = S->x;
       // o_proj's gather (qlinear.py:275): copy x to shared memory first (coalesced, one L2 round trip; the buffer aliases
@@ -427,14 +435,13 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       const __half* nw = S->norm_w;
       const int live_k = S->nchunks * 32;
       const int nitems = M * ns * 8;
-      constexpr int kKeep = 2;
-      uint4 keep[kKeep][2];
-      float mx0 = 0.f, mx1 = 0.f, ss0 = 0.f, ss1 = 0.f;
-      // item = (batch row b, step, chunk tt, hs): the 16 columns k0 .. k0+7 and k0+16 .. k0+23, k0 = 128 step + 32 tt + 8 hs
-      auto load_item = [&](int it, uint4& v0, uint4& v1, int& b, bool& live) {
+      const int npass = (nitems + kDThreads - 1) / kDThreads;
+      // item = (batch row b, step, chunk tt, hs): the 16 columns k0 .. k0+7 and k0+16 .. k0+23, k0 = 128 step + 32 tt + 8 hs;
+      // the 8 items of a step sit in 8 adjacent lanes, which agree on the step's sum and maximum by shuffles
+      auto load_item = [&](int it, uint4& v0, uint4& v1, int& b, int& st, bool& live) {
         const int sb = it >> 3;
         b = sb / ns;
-        const int st = sb - b * ns;
+        st = sb - b * ns;
         const int k0 = st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8;
         live = it < nitems && k0 < live_k;
         v0 = v1 = make_uint4(0u, 0u, 0u, 0u);
@@ -450,63 +457,14 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             v0 = d_ldcg128(xr + k0);
             v1 = d_ldcg128(xr + k0 + 16);
           }
-          if (nw) {
-            // RMSNorm on the way in (HF LlamaRMSNorm: weight * (x * rsqrt(mean x^2 + eps)).to(fp16)): here only the
-            // sum of squares; the scaling happens in pass B
-            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            float ss = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
-            if (b == 0) ss0 += ss; else ss1 += ss;
-          }
         }
       };
-      auto absmax_item = [&](const uint4& v0, const uint4& v1) {
-        __half2 a = __habs2(*reinterpret_cast<const __half2*>(&v0.x));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v0.y)));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v0.z)));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v0.w)));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.x)));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.y)));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.z)));
-        a = __hmax2(a, __habs2(*reinterpret_cast<const __half2*>(&v1.w)));
-        return fmaxf(__low2float(a), __high2float(a));
-      };
-      // x * norm weight (fp32 product of the fp16 inputs), used for the bound of |normalised x|
-      auto scaled_absmax_item = [&](const uint4& v0, const uint4& v1, int it) {
-        const int sb = it >> 3, b = sb / ns, st = sb - b * ns;
-        const int k0 = st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8;
-        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        float mxv = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = k0 + (j < 4 ? 2 * j : 16 + 2 * (j - 4));
-          const int c0 = gat ? gat[k] : k, c1 = gat ? gat[k + 1] : k + 1;
-          const float2 f = half2_bits_to_float2(w[j]);
-          mxv = fmaxf(mxv, fmaxf(fabsf(f.x * __half2float(nw[c0])), fabsf(f.y * __half2float(nw[c1]))));
-        }
-        return mxv;
-      };
-      const int npass = (nitems + kDThreads - 1) / kDThreads;
-      // pass A: all loads of the thread's first kKeep items are in flight together (one L2 round trip)
-#pragma unroll
-      for (int q = 0; q < kKeep; ++q) {
-        int b; bool live;
-        load_item(q * kDThreads + tid, keep[q][0], keep[q][1], b, live);
-        if (q < npass && live) {
-          const float v = nw ? scaled_absmax_item(keep[q][0], keep[q][1], q * kDThreads + tid) : absmax_item(keep[q][0], keep[q][1]);
-          if (b == 0) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-        }
-      }
-      for (int q = kKeep; q < npass; ++q) {
-        uint4 v0, v1; int b; bool live;
-        load_item(q * kDThreads + tid, v0, v1, b, live);
-        if (live) {
-          const float v = nw ? scaled_absmax_item(v0, v1, q * kDThreads + tid) : absmax_item(v0, v1);
-          if (b == 0) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-        }
-      }
-      // the outlier activations (fp16 path): loaded here, stored after the reduction
+      // the loads of the first two passes and of the outlier activations are in flight together
+      uint4 k0a, k0b, k1a, k1b;
+      int kb0, kb1, ks0, ks1;
+      bool kl0, kl1;
+      load_item(tid, k0a, k0b, kb0, ks0, kl0);
+      load_item(kDThreads + tid, k1a, k1b, kb1, ks1, kl1);
       const int nxo = M * (r >> 3);
       uint4 xo_v = make_uint4(0u, 0u, 0u, 0u);
       const int xo_tid = kDThreads - 1 - tid;              // the threads the digit items use least
@@ -520,83 +478,53 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         } else {
           xo_v = d_ldcg128(xr + K - r + 8 * jj);
         }
-        if (nw) {
-          const uint32_t w[4] = {xo_v.x, xo_v.y, xo_v.z, xo_v.w};
+      }
+      float rs0 = 1.f, rs1 = 1.f;
+      if (nw) {
+        // RMSNorm on the way in (HF LlamaRMSNorm / kernel/layernorm/layernorm.cu:25-51): the row's sum of squares needs the
+        // whole row: one CTA-wide reduction (only for stages with a norm)
+        float ss0 = 0.f, ss1 = 0.f;
+        auto sumsq = [&](const uint4& v0, const uint4& v1, int b) {
+          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
           float ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+          for (int j = 0; j < 8; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
           if (b == 0) ss0 += ss; else ss1 += ss;
+        };
+        if (kl0) sumsq(k0a, k0b, kb0);
+        if (kl1) sumsq(k1a, k1b, kb1);
+        for (int q = 2; q < npass; ++q) {
+          uint4 v0, v1; int b, st; bool live;
+          load_item(q * kDThreads + tid, v0, v1, b, st, live);
+          if (live) sumsq(v0, v1, b);
         }
-      }
-      dec_stamp(L, s, 4);
-      // CTA-wide maximum (and sum of squares) per batch row
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
-      }
-      if (nw) {
+        if (xo_tid < nxo) sumsq(xo_v, make_uint4(0u, 0u, 0u, 0u), xo_tid / (r >> 3));
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
           ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
           ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
         }
-      }
-      if (lane == 0) { red[warp * 4 + 0] = mx0; red[warp * 4 + 1] = mx1; red[warp * 4 + 2] = ss0; red[warp * 4 + 3] = ss1; }
-      d_consumer_sync();
-      mx0 = mx1 = ss0 = ss1 = 0.f;
+        if (lane == 0) { red[warp * 4 + 2] = ss0; red[warp * 4 + 3] = ss1; }
+        d_consumer_sync();
+        ss0 = ss1 = 0.f;
 #pragma unroll
-      for (int w = 0; w < kDWarps; ++w) {
-        mx0 = fmaxf(mx0, red[w * 4 + 0]); mx1 = fmaxf(mx1, red[w * 4 + 1]);
-        ss0 += red[w * 4 + 2]; ss1 += red[w * 4 + 3];
-      }
-      float rs0 = 1.f, rs1 = 1.f;
-      if (nw) {
+        for (int w = 0; w < kDWarps; ++w) { ss0 += red[w * 4 + 2]; ss1 += red[w * 4 + 3]; }
         rs0 = rsqrtf(ss0 / (float)K + S->norm_eps);
         rs1 = rsqrtf(ss1 / (float)K + S->norm_eps);
-        // |w * fp16(x * rs)| <= |w x| rs (1 + 2^-10), rounded once more to fp16: bound with a margin
-        mx0 *= rs0 * 1.002f; mx1 *= rs1 * 1.002f;
       }
-      // 2^e > max|x|;  X = rint(x 2^(29-e)), |X| < 2^29;  digit d weighs 2^(e-29+8d), and 1/16 for the nibble trick
-      const int e0 = mx0 > 0.f ? (int)((__float_as_uint(mx0) >> 23) & 0xff) - 126 : -100;
-      const int e1 = mx1 > 0.f ? (int)((__float_as_uint(mx1) >> 23) & 0xff) - 126 : -100;
-      const float sc0 = e0 > -100 ? __uint_as_float((uint32_t)(127 + 29 - e0) << 23) : 0.f;
-      const float sc1 = e1 > -100 ? __uint_as_float((uint32_t)(127 + 29 - e1) << 23) : 0.f;
-      if (tid < 8) {
-        // coef[2t], coef[2t+1]: what lane t of a quad multiplies its two accumulator columns with at a flush
-        const int b = tid >> 2, d = tid & 3;
-        const int e = b ? e1 : e0;
-        float c = (e > -100 && b < M) ? __uint_as_float((uint32_t)(127 + e - 29 + 8 * d - 4) << 23) : 0.f;
-        if (M == 1 && tid == 4) c = 1.f;            // batch 1: lane t = 2 carries the zero-point sums unscaled
-        coef[tid] = c;
-      }
-      dec_stamp(L, s, 5);
-      // pass B: digits
+      dec_stamp(L, s, 4);
+      // the reference's two roundings: (x * rs).to(fp16), then * weight in fp16
+      auto normed = [&](float v, int col, float rs) { return __half2float(__hmul(nw[col], __float2half_rn(v * rs))); };
       for (int q = 0; q < npass; ++q) {
         const int it = q * kDThreads + tid;
-        uint4 v0, v1; int b; bool live;
-        if (q < kKeep) {
-          // select the kept pair without dynamic register indexing
-          v0 = keep[0][0]; v1 = keep[0][1];
-#pragma unroll
-          for (int j = 1; j < kKeep; ++j)
-            if (q == j) { v0 = keep[j][0]; v1 = keep[j][1]; }
-          const int sb = it >> 3;
-          b = sb / ns;
-          const int st = sb - b * ns;
-          live = it < nitems && (st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8) < live_k;
-        } else {
-          float sv0 = ss0, sv1 = ss1;                    // (load_item adds to the sums: keep them)
-          load_item(it, v0, v1, b, live);
-          ss0 = sv0; ss1 = sv1;
-        }
+        uint4 v0, v1; int b, st; bool live;
+        if (q == 0) { v0 = k0a; v1 = k0b; b = kb0; st = ks0; live = kl0; }
+        else if (q == 1) { v0 = k1a; v1 = k1b; b = kb1; st = ks1; live = kl1; }
+        else load_item(it, v0, v1, b, st, live);
         const bool valid = it < nitems;
-        const int sb = valid ? (it >> 3) : 0;
-        const int st = sb - (sb / ns) * ns;
         const int tt = (it >> 1) & 3, hs = it & 1;
         const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         float2 f[8];
-        float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = half2_bits_to_float2(w[j]);
         if (nw && live) {
@@ -606,21 +534,28 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           for (int j = 0; j < 8; ++j) {
             const int k = k0 + (j < 4 ? 2 * j : 16 + 2 * (j - 4));
             const int c0 = gat ? gat[k] : k, c1 = gat ? gat[k + 1] : k + 1;
-            // the reference's two roundings: (x * rs).to(fp16), then * weight in fp16
-            const __half h0 = __hmul(nw[c0], __float2half_rn(f[j].x * rs)), h1 = __hmul(nw[c1], __float2half_rn(f[j].y * rs));
-            f[j] = make_float2(__half2float(h0), __half2float(h1));
+            f[j] = make_float2(normed(f[j].x, c0, rs), normed(f[j].y, c1, rs));
           }
         }
+        float sum = 0.f, mx = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += f[j].x + f[j].y;
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        for (int j = 0; j < 8; ++j) {
+          sum += f[j].x + f[j].y;
+          mx = fmaxf(mx, fmaxf(fabsf(f[j].x), fabsf(f[j].y)));
+        }
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
         if (valid) {
-          const float sc = b ? sc1 : sc0;
+          // 2^e > mx;  X = rint(x 2^(22-e)) by the magic-number add (|X| < 2^22): bits(fma(x, sc, 1.5 2^23)) = 0x4B400000 + X.
+          // Z = X + 0x808080 has unsigned bytes b_i with X = sum (b_i - 128) 256^i: the signed digits are the bytes of Z ^ 0x808080.
+          const int e = mx > 0.f ? (int)((__float_as_uint(mx) >> 23) & 0xff) - 126 : -100;
+          const float sc = e > -100 ? __uint_as_float((uint32_t)(127 + 22 - e) << 23) : 0.f;
           auto digits = [&](float v) {
-            const int X = __float2int_rn(v * sc);
-            return (uint32_t)(X + 0x00808080) ^ 0x00808080u;       // bytes = signed digits d0..d3
+            const int bits = __float_as_int(fmaf(v, sc, 12582912.f));
+            return (uint32_t)(bits + (0x00808080 - 0x4B400000)) ^ 0x00808080u;
           };
           uint32_t dg[16];
 #pragma unroll
@@ -630,7 +565,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           // position hs.  Lane t's 16-byte row of (hs, column) holds its four chunks' words, index tt.
           const uint32_t dst = xdig + (uint32_t)st * XSTEP + (uint32_t)hs * XHALF + (uint32_t)(4 * b) * 64 + (uint32_t)tt * 4;
 #pragma unroll
-          for (int d = 0; d < 4; ++d) {
+          for (int d = 0; d < 3; ++d) {
             const uint32_t sel = 0x0040u + 0x11u * (uint32_t)d;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -638,7 +573,11 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
               asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + (uint32_t)(d * 64 + c * 16)), "r"(ww) : "memory");
             }
           }
-          if ((it & 7) == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum + (uint32_t)(st * 8 + b * 4)), "f"(sum) : "memory");
+          if ((it & 7) == 0) {
+            // per step and batch row: {sum of x, weight of digit 0 = 2^(e-22) / 16 (the nibble trick's 16 q)}
+            const float cg = e > -100 ? __uint_as_float((uint32_t)(127 + e - 22 - 4) << 23) : 0.f;
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xsum + (uint32_t)(st * 16 + b * 8)), "f"(sum), "f"(cg) : "memory");
+          }
         }
       }
       dec_stamp(L, s, 6);
@@ -668,6 +607,21 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       const int KB = (ns + kKB - 1) / kKB;
       const uint32_t xo_lane = xo + (uint32_t)((gx * r + 2 * t) * 2);
       uint4 xe = make_uint4(0u, 0u, 0u, 0u), xq = xe, xe2 = xe, xq2 = xe;
+      float2 xs0 = make_float2(0.f, 0.f), xs1 = xs0;
+      // B fragments (digit bytes), group sum and digit weight of one step
+      auto load_x = [&](int gs, uint4& xe_, uint4& xq_, float2& xs) {
+        const uint32_t xc = xdig_lane + (uint32_t)gs * XSTEP;
+        d_lds128_if(xe_, xc, has_col);
+        d_lds128_if(xq_, xc + XHALF, has_col);
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xs.x), "=f"(xs.y) : "r"(xsum + (uint32_t)(gs * 16 + (M == 2 ? (t >> 1) * 8 : 0))) : "memory");
+      };
+      // single-k-block stages (K <= 4096 + r): a warp works on the same two steps of every tile: their B operands are
+      // loaded once per stage and stay in registers
+      const bool bcache = KB == 1;
+      if (bcache) {
+        if (warp < ns) load_x(warp, xe, xq, xs0);
+        if (warp + kDWarps < ns) load_x(warp + kDWarps, xe2, xq2, xs1);
+      }
 #pragma unroll 1
       for (int j = 0; j < R.ntiles; ++j) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};    // rows 2g, 2g+1 x accumulator columns 2t, 2t+1: sum over groups of scale * P
@@ -687,30 +641,29 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           // (low nibbles q, high nibbles 16 q: both valid u8), 4 IMMA with exact s32 accumulation; 16 lo + hi = 16 sum(q X).
           // A warp's two steps of the block (warp, warp + 16) are loaded together and then computed: twice the loads
           // in flight per warp.
-          auto load_step = [&](int st, uint32_t (&a0)[4], uint32_t (&a1)[4], uint4& xe_, uint4& xq_, uint32_t& sw, uint32_t& zw, float& xs) {
-            const int gs = kb * kKB + st;
+          auto load_step = [&](int st, uint32_t (&a0)[4], uint32_t (&a1)[4], uint4& xe_, uint4& xq_, uint32_t& sw, uint32_t& zw, float2& xs) {
             d_ldmatrix_x4(a0, sbase + laneA + (uint32_t)(st * 256));
             d_ldmatrix_x4(a1, sbase + laneA + (uint32_t)(st * 256 + 128));
-            const uint32_t xc = xdig_lane + (uint32_t)gs * XSTEP;
-            d_lds128_if(xe_, xc, has_col);
-            d_lds128_if(xq_, xc + XHALF, has_col);
+            if (!bcache) load_x(kb * kKB + st, xe_, xq_, xs);
             sw = d_lds32(sbase + laneS + (uint32_t)(st * 16));
             zw = M == 2 ? d_lds32(sbase + laneS + (uint32_t)(st * 16 + 8)) : 0u;
-            xs = d_ldsf(xsum + (uint32_t)(gs * 8 + (M == 2 ? (t >> 1) * 4 : 0)));
           };
-          auto math_step = [&](const uint32_t (&a0)[4], const uint32_t (&a1)[4], const uint4& xe_, const uint4& xq_, uint32_t sw, uint32_t zw, float xs) {
+          auto math_step = [&](const uint32_t (&a0)[4], const uint32_t (&a1)[4], const uint4& xe_, const uint4& xq_, uint32_t sw, uint32_t zw, float2 xs2) {
+            const float xs = xs2.x;
             constexpr uint32_t kLoM = 0x0f0f0f0fu, kHiM = 0xf0f0f0f0u;
             int lo[4], hi[4];
             d_imma0(lo, a0[0] & kLoM, a0[1] & kLoM, a0[2] & kLoM, a0[3] & kLoM, xe_.x, xe_.y);
             d_imma0(hi, a0[0] & kHiM, a0[1] & kHiM, a0[2] & kHiM, a0[3] & kHiM, xq_.x, xq_.y);
             d_imma(lo, a1[0] & kLoM, a1[1] & kLoM, a1[2] & kLoM, a1[3] & kLoM, xe_.z, xe_.w);
             d_imma(hi, a1[0] & kHiM, a1[1] & kHiM, a1[2] & kHiM, a1[3] & kHiM, xq_.z, xq_.w);
-            const float2 sc = half2_bits_to_float2(sw);
+            float2 sc = half2_bits_to_float2(sw);
             float f0 = (float)(lo[0] * 16 + hi[0]), f2 = (float)(lo[2] * 16 + hi[2]);
             const float f1 = (float)(lo[1] * 16 + hi[1]), f3 = (float)(lo[3] * 16 + hi[3]);
             if (M == 1) {
               if (zlane) { f0 = xs; f2 = xs; }               // scaled zero x group sum of x in the zero-point lane
+              else { sc.x *= xs2.y; sc.y *= xs2.y; }         // digit lanes: scale x the step's digit weight
             } else {
+              sc.x *= xs2.y; sc.y *= xs2.y;
               const float2 zz = half2_bits_to_float2(zw);
               zacc0 = fmaf(zz.x, xs, zacc0);
               zacc1 = fmaf(zz.y, xs, zacc1);
@@ -722,7 +675,6 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           };
           if (warp < nsb && !(L.debug & 1)) {
             uint32_t a0[4], a1[4], b0[4], b1[4], sw0, sw1 = 0, zw0, zw1 = 0;
-            float xs0, xs1 = 0.f;
             const bool two = warp + kDWarps < nsb;
             load_step(warp, a0, a1, xe, xq, sw0, zw0, xs0);
             if (two) load_step(warp + kDWarps, b0, b1, xe2, xq2, sw1, zw1, xs1);
@@ -747,7 +699,9 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         }
         {
           // end of the tile: accumulator columns -> one value per (row, batch row), to this warp's slice of the tile
-          const float c0 = coef[2 * t], c1 = coef[2 * t + 1];
+          // digit columns of a batch row weigh 1, 256, 65536 (the fourth column is unused); M = 1: lane t = 2 is the zero-point lane
+          const float c0 = (M == 1 ? (t == 0 ? 1.f : (t == 1 ? 65536.f : (t == 2 ? 1.f : 0.f))) : ((t & 1) ? 65536.f : 1.f));
+          const float c1 = (M == 1 ? (t == 0 ? 256.f : 0.f) : ((t & 1) ? 0.f : 256.f));
           float v1 = fmaf(c0, acc[0], c1 * acc[1]), v2 = fmaf(c0, acc[2], c1 * acc[3]);
           v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
           v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
@@ -1027,7 +981,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   L.sarea = kSideSteps + 8 * max_r;
   L.slot = (int)(((size_t)(kSlotW + 4 * L.sarea) + 127) & ~(size_t)127);
   const size_t xdig = (size_t)max_steps * 128 * 4 * m;
-  const size_t xsum = (size_t)max_steps * 8 + 16;
+  const size_t xsum = (size_t)max_steps * 16 + 16;
   const size_t xo = (size_t)m * max_r * 2 + 16;
   const size_t part = (size_t)max_tiles * kDWarps * m * 16 * sizeof(float);
   const size_t misc = 2048;
@@ -1040,6 +994,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   L.nslots = nslots;
   size_t off = (size_t)nslots * (size_t)L.slot;
   L.xdig = (int)off; off += (xdig + 127) & ~(size_t)127;
+  L.xdig_bytes = (int)((xdig + 127) & ~(size_t)127);
   L.xsum = (int)off; off += (xsum + 127) & ~(size_t)127;
   L.xo = (int)off; off += (xo + 127) & ~(size_t)127;
   L.part = (int)off; off += (part + 127) & ~(size_t)127;

@@ -35,8 +35,7 @@ def main():
     t0 = t[0, :, 0].min()
     rel = (t - t0) / 1e3     # us
     names = ["qkv", "o", "gateup", "down"]
-    agg = {k: {"wait": [], "stage_x": [], "consume": [], "reduce_store": [], "x_loads_max": [], "x_reduce": [],
-               "x_digits": [], "x_tail": []} for k in names}
+    agg = {k: {"wait": [], "stage_x": [], "consume": [], "reduce_store": [], "x_loads_max": [], "x_digits": [], "x_tail": []} for k in names}
     for s in range(1, n):
         k = names[s % 4]
         for c in range(4):
@@ -45,8 +44,7 @@ def main():
             agg[k]["consume"].append(rel[s, c, 2] - rel[s, c, 1])
             agg[k]["reduce_store"].append(rel[s, c, 3] - rel[s, c, 2])
             agg[k]["x_loads_max"].append(rel[s, c, 4] - rel[s, c, 0])
-            agg[k]["x_reduce"].append(rel[s, c, 5] - rel[s, c, 4])
-            agg[k]["x_digits"].append(rel[s, c, 6] - rel[s, c, 5])
+            agg[k]["x_digits"].append(rel[s, c, 6] - rel[s, c, 4])
             agg[k]["x_tail"].append(rel[s, c, 1] - rel[s, c, 6])
     out = {k: {kk: round(float(np.median(vv)), 2) for kk, vv in v.items()} for k, v in agg.items()}
     out["total_us"] = round(float(rel[n - 1, :, 3].max()), 1)
