@@ -280,7 +280,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const uint32_t bars = d_smem_u32(dsm + L.misc + 512);      // [nslots] "slot filled" mbarriers
   const uint32_t ebars = bars + 64;                          // [nslots] "slot consumed" mbarriers (16 warp arrivals)
   DecStage* pcache = reinterpret_cast<DecStage*>(dsm + L.misc + 768);     // descriptor of the producer's stage
-  DecStage* ccache = reinterpret_cast<DecStage*>(dsm + L.misc + 1280);    // descriptor of the stage being consumed
+  DecStage* ccache2 = reinterpret_cast<DecStage*>(dsm + L.misc + 1280);   // descriptors of the stage being consumed / the next one
   static_assert(sizeof(DecStage) <= 384 && sizeof(DecStage) % 4 == 0, "descriptor cache slots are 384 bytes");
   constexpr int kStageWords = (int)(sizeof(DecStage) / 4);
 
@@ -295,7 +295,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   // dependent L2 round trips per block is what made the first versions of this kernel slow: they are read from a
   // shared-memory copy instead)
   if (tid >= 32 && tid < 32 + kStageWords)
-    reinterpret_cast<uint32_t*>(ccache)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s_begin)[tid - 32];
+    reinterpret_cast<uint32_t*>(ccache2)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s_begin)[tid - 32];
   // the barrier counter only grows; `base` is its value when every CTA of this launch has started
   const unsigned base = *reinterpret_cast<volatile unsigned*>(sync + 1);
   __syncthreads();
@@ -386,12 +386,14 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
 
 #pragma unroll 1
   for (int s = s_begin; s < s_end; ++s) {
-    const DecStage* S = ccache;              // (the copy of stage s; complete after the barrier below / the initial sync)
+    const DecStage* S = reinterpret_cast<const DecStage*>(reinterpret_cast<const uint8_t*>(ccache2) + ((s - s_begin) & 1) * 384);
+    // (the copy of stage s; complete after the barrier below / the initial sync)
 
     if (s > s_begin) {
       // ---- stage boundary: every CTA has stored its rows of the previous stage -------------------------------
       if (tid == 0) {
         const unsigned want = base + (unsigned)(s - s_begin) * (unsigned)ncta;
+        // (polling with relaxed loads and one acquire fence at the end was measured slower: +0.4 us per stage)
         unsigned got;
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(sync) : "memory");
@@ -632,7 +634,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           const uint32_t sbase = ring + (uint32_t)cslot * (uint32_t)L.slot;
           // wait for the block (lane 0 polls, so that the loop is warp-uniform); meanwhile help refilling free slots
           const long long tw0 = dbg ? clock64() : 0;
-          const bool ready0 = d_mbar_test(bars + 8 * cslot, cpar);
+          const bool ready0 = dbg ? d_mbar_test(bars + 8 * cslot, cpar) : true;
           d_mbar_wait(bars + 8 * cslot, cpar);               // the block's bytes have landed (every lane acquires them)
           const long long tw1 = dbg ? clock64() : 0;
           if (dbg) { dbg_wait += tw1 - tw0; ++dbg_nblocks; if (!ready0) ++dbg_nwaited; }
@@ -761,11 +763,13 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       }
     }
     if (s + 1 < s_end) {
+      // (one signal per CTA: one signal per warp was measured slower -- 16 x 148 atomics on one address per stage)
       d_consumer_sync();
       if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
-      // the next stage's descriptor (read only after the barrier's __syncthreads)
+      // the next stage's descriptor, into the other buffer (its L2 round trip overlaps the wait at the barrier)
       if (tid >= 32 && tid < 32 + kStageWords)
-        reinterpret_cast<uint32_t*>(ccache)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s + 1)[tid - 32];
+        reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ccache2) + ((s + 1 - s_begin) & 1) * 384)[tid - 32] =
+            reinterpret_cast<const uint32_t*>(stages + s + 1)[tid - 32];
     }
     dec_stamp(L, s, 3);
   }
@@ -984,7 +988,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   const size_t xsum = (size_t)max_steps * 16 + 16;
   const size_t xo = (size_t)m * max_r * 2 + 16;
   const size_t part = (size_t)max_tiles * kDWarps * m * 16 * sizeof(float);
-  const size_t misc = 2048;
+  const size_t misc = 2560;
   const size_t fixed = ((xdig + 127) & ~(size_t)127) + ((xsum + 127) & ~(size_t)127) + ((xo + 127) & ~(size_t)127) +
                        ((part + 127) & ~(size_t)127) + misc;
   if (fixed + 2 * (size_t)L.slot > kDSmemMax) return QEFT_E_UNSUPPORTED;
