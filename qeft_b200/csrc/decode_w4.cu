@@ -982,7 +982,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   }
   DecLayout L;
   L.slot_s = kSlotW;
-  L.sarea = kSideSteps + 8 * max_r;
+  L.sarea = kSideSteps + 8 * max_r + 16;      // + 16: the four qweight rows' scale words fall into different banks
   L.slot = (int)(((size_t)(kSlotW + 4 * L.sarea) + 127) & ~(size_t)127);
   const size_t xdig = (size_t)max_steps * 128 * 4 * m;
   const size_t xsum = (size_t)max_steps * 16 + 16;

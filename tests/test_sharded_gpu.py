@@ -161,3 +161,127 @@ def test_launch_on_a_device_that_is_not_current():
     rel = lambda a, b: float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / np.max(np.abs(b.astype(np.float64))))  # noqa: E731
     assert rel(y.cpu().numpy(), want) <= 1e-3
     assert rel(ym.cpu().numpy(), oracle.forward(xm, L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], None)) <= 1e-3
+
+
+# ---- the acquire-then-consume path: launch i+1 READS the gathered buffer of launch i ---------------------------------
+def _chain_worker(rank, world, port, q):
+    """Three column-sharded GEMVs chained through their gathered buffers (x of launch i+1 = gathered y of launch i, ordered
+    only by the arrival counter under programmatic dependent launch), eagerly and replayed from a CUDA graph, against
+    the same chain with local kernels + NCCL all-gathers.  Exercises the coherent x loads of launches with a wait flag
+    (a gathered x must not be read through the read-only path)."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from qeft_b200 import _lib, qeft_cuda
+        from qeft_b200.modelutils import shard_layer_tensors
+        from qeft_b200.synth import synth_tensors
+        dev = f"cuda:{rank}"
+        H, r, G, nl = 1024, 128, 128, 3
+        # small weights so that three chained layers stay in fp16 range
+        fulls = []
+        for i in range(nl):
+            t = synth_tensors(H, H, r, G, seed=900 + i, device=dev)
+            t["scales"] = (t["scales"].float() * 0.05).half()
+            t["scaled_zeros"] = (t["scaled_zeros"].float() * 0.05).half()
+            t["oweight"] = (t["oweight"].float() * 0.05).half()
+            t["oweight_interleaved"] = qeft_cuda.interleave_oweight(t["oweight"])
+            fulls.append(t)
+        shards = [shard_layer_tensors(t, rank, world, multiple=16) for t in fulls]
+        w = H // world
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(4)
+        x0 = torch.randn((1, H), device=dev, generator=gen).half()
+
+        def part(t):
+            return {"qweight": t["qweight"], "scales": t["scales"], "scaled_zeros": t["scaled_zeros"],
+                    "oweight": t["oweight_interleaved"], "N": w}
+
+        # reference chain: local kernel + NCCL all-gather
+        ref = []
+        x = x0
+        for t in shards:
+            y = qeft_cuda.gemv_w4_multi(x, [part(t)], 1, H, r, G, ow_layout=_lib.OW_INTERLEAVED, pdl=False)[0]
+            full = torch.empty((1, H), dtype=torch.float16, device=dev)
+            dist.all_gather_into_tensor(full.view(-1), y.reshape(-1).contiguous())
+            ref.append(full)
+            x = full
+        torch.cuda.synchronize()
+
+        # fused chain through symmetric memory: flags first, then the gathered buffers
+        flag_bytes = 256
+        buf = symm_mem.empty((flag_bytes + nl * 2 * H,), dtype=torch.uint8, device=dev)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
+        gathers, outs, prev = [], [], None
+        for i in range(nl):
+            g = _lib.Gather()
+            g.nranks, g.y_ld = world, H
+            off = flag_bytes + i * 2 * H
+            for pr in range(world):
+                g.y_peer[pr][0] = hdl.buffer_ptrs[pr] + off + 2 * rank * w
+                g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * i
+            g.local_count = None
+            g.wait_flag = prev
+            g.epoch = epoch.data_ptr()
+            prev = buf.data_ptr() + 4 * i
+            gathers.append(g)
+            outs.append(buf[off:off + 2 * H].view(torch.float16).view(1, H))
+        hdl.barrier()
+
+        def step():
+            epoch.add_(1)
+            x = x0
+            for t, g, o in zip(shards, gathers, outs):
+                qeft_cuda.gemv_w4_multi_gather(x, [part(t)], 1, H, r, G, g, ow_layout=_lib.OW_INTERLEAVED, pdl=True)
+                x = o
+            qeft_cuda.gather_wait(prev, epoch, world)
+
+        ok = True
+        graph = None
+        for mode in ("eager", "eager", "graph", "graph", "graph"):
+            if mode == "graph" and graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    step()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                dist.barrier()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step()
+            if mode == "eager":
+                step()
+            else:
+                graph.replay()
+            torch.cuda.synchronize()
+            dist.barrier()
+            for o, want in zip(outs, ref):
+                ok = ok and torch.equal(o, want)
+            dist.barrier()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_chained_gathered_input_equals_nccl_chain():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chain_worker, args=(rank, world, port, q)) for rank in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
