@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-gemm", action="store_true", help="skip the prefill GEMM / backward extras (M=2048 TFLOP/s)")
     ap.add_argument("--no-program", action="store_true",
                     help="N = 1: the round-1 chain of 4 x layers PDL launches instead of the persistent decode program")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same workload on rank 0")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the gathered-output parity check before timing")
     return ap.parse_args()
 
@@ -292,7 +293,7 @@ def sharded_parity_check(stack, world, rank, gather_mode):
     buffer of all four launch groups of the first and of the last decoder block against
       (a) this rank's local kernel outputs all-gathered by NCCL (same kernel, same row partition): bit-equal, and
       (b) the UNSHARDED kernel (qeft_gemv_w4_multi on the weights of all ranks, gathered here for the check, same x):
-          equal to one fp16 ulp (the row partition changes the fp32 summation order of a row's K-slices).
+          equal to one fp16 ulp + 4e-6 rms (the row partition changes the fp32 summation order of a row's K-slices).
     Returns {"groups": n, "ok": bool, ...}; the caller exits non-zero when not ok."""
     import torch
     import torch.distributed as dist
@@ -306,9 +307,11 @@ def sharded_parity_check(stack, world, rank, gather_mode):
     checked, bad_a, bad_b, worst_ulp = 0, 0, 0, 0.0
 
     def gather_cat(t, dim):
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t.contiguous())
-        return torch.cat(parts, dim=dim).contiguous()
+        t = t.contiguous()
+        raw = t.view(torch.uint8)                        # (NCCL has no int16: gather the bytes)
+        parts = [torch.empty_like(raw) for _ in range(world)]
+        dist.all_gather(parts, raw)
+        return torch.cat([p.view(t.dtype).view(t.shape) for p in parts], dim=dim).contiguous()
 
     for li in sorted({0, stack.nlayers - 1}):
         blk = stack.blocks[li]
@@ -339,8 +342,9 @@ def sharded_parity_check(stack, world, rank, gather_mode):
             want_b = torch.cat([torch.cat([y.reshape(-1)[p * blk[n]["N"]:(p + 1) * blk[n]["N"]] for y, n in zip(full, names)])
                                 for p in range(world)]).view(world, -1)
             d = (want_b.float() - got.float()).abs()
-            ulp = torch.clamp(want_b.float().abs(), min=2.0 ** -14) * 2.0 ** -10      # one fp16 ulp at |want|
-            worst = float((d / ulp).max())
+            # one fp16 ulp at |want| (a rounding flip) + the fp32 summation-order noise of a row (~1e-6 of the rows' rms)
+            tol = torch.clamp(want_b.float().abs(), min=2.0 ** -14) * 2.0 ** -10 + 4e-6 * want_b.float().pow(2).mean().sqrt()
+            worst = float((d / tol).max())
             worst_ulp = max(worst_ulp, worst)
             bad_b += int(worst > 1.0)
             del full_parts, full
@@ -396,7 +400,14 @@ def run_ours(args):
             os._exit(3)
     use_program = world == 1 and not args.no_program and not args.no_fused and args.batch <= 2
     if use_program:
-        stack.enable_program()       # one persistent cooperative launch per token (csrc/decode_w4.cu)
+        try:
+            stack.enable_program()   # one persistent cooperative launch per token (csrc/decode_w4.cu)
+            stack.step_eager()
+            torch.cuda.synchronize()
+        except RuntimeError as e:    # (a box that cannot co-schedule 148 CTAs: the launch chain still measures the path)
+            print(f"bench.py: decode program unavailable ({e}); timing the launch chain", file=sys.stderr)
+            stack.program = None
+            use_program = False
     if not args.no_graph:
         stack.capture()
 
@@ -495,6 +506,44 @@ def run_ours(args):
             # configs[3]: the 13B shapes of the fine-tuning step (fwd + dX + dOW per linear, M = 2048)
             extra["finetune_13b"] = bench_gemm("13b")
         stack = None
+    if world > 1 and rank == 0 and not args.no_single:
+        # strong-scaling reference: the SAME workload (all layers unsharded) on this rank's GPU alone, through our kernels
+        try:
+            single = PackedDecoderStack(model, layers=args.layers, fused=True, pdl=True, shard=(0, 1), batch=args.batch,
+                                        device=f"cuda:{local}", fast_synth=True)
+
+            def t_steps(fn, n=5):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / n
+
+            nb = single.algorithmic_bytes_per_step()
+            single.capture()
+            ms_chain1 = t_steps(single.step)
+            res = {"ms_per_step_launch_chain": ms_chain1, "GBps_launch_chain": nb / ms_chain1 / 1e6}
+            try:
+                single.graph = None
+                single.enable_program()
+                ms_prog1 = t_steps(single.step_eager)
+                res.update({"ms_per_step_program": ms_prog1, "GBps_program": nb / ms_prog1 / 1e6})
+            except RuntimeError as e:
+                res["program"] = f"unavailable: {e}"
+            best = min(v for k, v in res.items() if k.startswith("ms_per_step"))
+            res.update({"ms_per_step": best, "speedup_of_this_run": best / (ms / args.steps),
+                        "strong_scaling_efficiency": best / (ms / args.steps) / world,
+                        "what": f"llama2-{model}, all layers unsharded on one B200 (rank 0), same kernels"})
+            extra["single_gpu_same_workload"] = res
+            del single
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            extra["single_gpu_same_workload"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if not args.no_gemm and world > 1:
         # configs[4], prefill half: the same shapes, M = 2048 tokens, every linear column-sharded; all three exchanges
         stack.graph = None
@@ -528,8 +577,8 @@ def run_ours(args):
                 "layers": workload_layers, "persistent_program": bool(use_program),
             },
             "decode_tok_s": args.batch * 1e3 / ms_step,
-            "decode_tok_s_note": "packed linears only (224 QuantLinear of the 32 blocks fed from fixed activation buffers); "
-                                 "attention, norms, embeddings and lm_head are not part of this path (SURVEY.md 8)",
+            "decode_tok_s_note": f"packed linears only ({7 * workload_layers} QuantLinear of the {workload_layers} blocks fed from fixed "
+                                 "activation buffers); attention, norms, embeddings and lm_head are not part of this path (SURVEY.md 8)",
             "clocks": clocks,
             "e2e": {"value": gbs_e2e, "unit": "GB/s", "tok_s": args.batch * 1e3 / (ms_e2e / args.steps),
                     "h2d_bytes_per_step": int(xh.numel() * 2 + xf.numel() * 2), "d2h_bytes_per_step": int(yh.numel() * 2)},

@@ -49,6 +49,10 @@ class PackedDecoderStack:
                                           device=self.device, o_proj=(name == "o"), fast=fast_synth)
                 blk[name]["N"] = N
             if r > 0:   # o_proj gathers its outlier channels to the back (qlinear.py:273-275): fused into the GEMV
+                # the OGR outlier indices are global: the same on every rank of a column-sharded layer
+                gi = torch.Generator(device=self.device)
+                gi.manual_seed(seed * 100003 + li * 16 + 999)
+                blk["o"]["outlieridx"] = torch.randperm(h, device=self.device, generator=gi)[:r].sort().values.to(torch.int32)
                 blk["o"]["reorder_ids32"] = sparse_to_dense_ids(blk["o"]["outlieridx"], h).to(torch.int32)
             self.blocks.append(blk)
         g = torch.Generator(device=self.device)
