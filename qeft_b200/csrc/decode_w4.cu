@@ -40,6 +40,9 @@ namespace qeft {
 constexpr int kDWarps = 16;
 constexpr int kDThreads = kDWarps * 32;       // consumer threads; one more warp only fills the ring
 constexpr int kDBlock = kDThreads + 32;
+#ifndef QEFT_DEC_MAXREG
+#define QEFT_DEC_MAXREG 96                      // 17 warps are allocated like 20: 640 x 96 = 61440 registers (104 and 120 do not launch)
+#endif
 #ifndef QEFT_DEC_STAGGER
 #define QEFT_DEC_STAGGER 16                     // qweight-row areas 16 bytes apart (mod 128): conflict-free ldmatrix (measured: bulk copies do not care)
 #endif
@@ -56,6 +59,9 @@ struct DecPart {
   const __half* ow;       // plain [N, r]
   const __half* bias;
   __half* y;              // [m, N]
+  uint2* y_ll;            // data-flow copy of y or null: [m * N / 2] words {two fp16 results, epoch of the run}
+  int ll_consumer;        // first stage that reads y_ll (the words are written only when that stage is part of the launch)
+  int pad1;
   const uint8_t* side;    // decode side table (built at program creation), per qweight row: [steps][scales of its 4 rows |
                           // scaled zeros of its 4 rows] then the fp16 outlier columns in MMA-fragment order
   int side_q;             // bytes per qweight row of `side`
@@ -94,6 +100,11 @@ struct DecStage {
   const int32_t* gather;      // [K] or null: x[:, gather[k]] is column k
   const __half* norm_w;       // [K] or null: RMSNorm weight applied to x on the way in
   const __half* residual;     // [m, N] or null: added to the (fp16-rounded) result of part 0
+  const uint2* x_ll;          // data-flow copy of x (the y_ll of the stage that produces it) or null
+  const uint2* res_ll;        // the same for the residual
+  int x_src, res_src;         // producing stages (the copies are valid only when those ran in THIS launch)
+  int force_barrier;          // a dependency on an earlier stage that is not linked by data-flow words
+  int nx_ll, nx_src;          // x_ll != null && !force_barrier / x_src of the NEXT stage (whether it waits at a barrier)
   float norm_eps;
   int nparts;
   int K, r;
@@ -258,9 +269,11 @@ __device__ __forceinline__ DecTiles dec_tiles(const DecStage* S, int cta, int nc
 // by conflict-free ldmatrix straight from the copied bytes), and the LAST warp to finish a block refills its slot with
 // the block nslots ahead in the sequence -- which may belong to a later stage: the stream does not stop at a stage
 // boundary, ~150 KB per SM stay in flight while the CTAs meet at the barrier and convert the next x.
-template <int M>
-__global__ void __launch_bounds__(kDBlock, 1)
-decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, unsigned* sync, const DecLayout L) {
+// LL: the launch uses data-flow words (stages ordered by polling their inputs); false compiles every such path out.
+template <int M, bool LL>
+__global__ void __maxnreg__(QEFT_DEC_MAXREG)
+decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, unsigned* sync, const DecLayout L,
+                 int nbar_total, int uses_ll) {
   extern __shared__ __align__(128) uint8_t dsm[];
   constexpr int NCOLS = 4 * M;
   constexpr uint32_t XSTEP = 128u * NCOLS;                   // digit bytes per 128-column step: [2 nibble halves][NCOLS][4 t][16 B]
@@ -280,8 +293,8 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const uint32_t bars = d_smem_u32(dsm + L.misc + 512);      // [nslots] "slot filled" mbarriers
   const uint32_t ebars = bars + 64;                          // [nslots] "slot consumed" mbarriers (16 warp arrivals)
   DecStage* pcache = reinterpret_cast<DecStage*>(dsm + L.misc + 768);     // descriptor of the producer's stage
-  DecStage* ccache2 = reinterpret_cast<DecStage*>(dsm + L.misc + 1280);   // descriptors of the stage being consumed / the next one
-  static_assert(sizeof(DecStage) <= 384 && sizeof(DecStage) % 4 == 0, "descriptor cache slots are 384 bytes");
+  DecStage* ccache2 = reinterpret_cast<DecStage*>(dsm + L.misc + 1536);   // descriptors of the stage being consumed / the next one
+  static_assert(sizeof(DecStage) <= 512 && sizeof(DecStage) % 4 == 0, "descriptor cache slots are 512 bytes");
   constexpr int kStageWords = (int)(sizeof(DecStage) / 4);
 
   if (tid == 0) {
@@ -298,6 +311,9 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     reinterpret_cast<uint32_t*>(ccache2)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s_begin)[tid - 32];
   // the barrier counter only grows; `base` is its value when every CTA of this launch has started
   const unsigned base = *reinterpret_cast<volatile unsigned*>(sync + 1);
+  // data-flow words carry the epoch of the run that wrote them (sync[2] = epoch of the last run that used them)
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(sync + 2) + 1u;
+  int nbar = 0;                                              // stage barriers passed so far
   __syncthreads();
 
   // the fourth digit column of every batch row is never written: it must read as zero (its accumulator column is unused)
@@ -305,7 +321,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   __syncthreads();
 
   // debug counters (QEFT_DECODE_STAMPS): warp 0 and warp 15 of CTA 0 and the producer warp, clock64 cycles
-  long long dbg_wait = 0, dbg_math = 0, dbg_issue = 0, dbg_fill = 0;
+  long long dbg_wait = 0, dbg_math = 0, dbg_issue = 0, dbg_fill = 0, dbg_prev = 0;
   int dbg_nissue = 0, dbg_nwaited = 0, dbg_nblocks = 0;
   const bool dbg = L.stamps != nullptr && cta == 0 && (warp == 0 || warp >= kDWarps - 1);
 
@@ -386,20 +402,23 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
 
 #pragma unroll 1
   for (int s = s_begin; s < s_end; ++s) {
-    const DecStage* S = reinterpret_cast<const DecStage*>(reinterpret_cast<const uint8_t*>(ccache2) + ((s - s_begin) & 1) * 384);
-    // (the copy of stage s; complete after the barrier below / the initial sync)
+    const DecStage* S = reinterpret_cast<const DecStage*>(reinterpret_cast<const uint8_t*>(ccache2) + ((s - s_begin) & 1) * 512);
 
-    if (s > s_begin) {
-      // ---- stage boundary: every CTA has stored its rows of the previous stage -------------------------------
+    // x produced by an earlier stage of this launch and linked by data-flow words: the stage polls the words it reads,
+    // no barrier.  Every other stage after the first waits until all CTAs have stored their rows of the previous one.
+    // (The descriptor copy of stage s was written before the previous stage's post-consume barrier.)
+    const bool ll_x = LL && S->x_ll != nullptr && S->x_src >= s_begin && !S->force_barrier;
+    if (s > s_begin && !ll_x) {
+      ++nbar;
       if (tid == 0) {
-        const unsigned want = base + (unsigned)(s - s_begin) * (unsigned)ncta;
+        const unsigned want = base + (unsigned)nbar * (unsigned)ncta;
         // (polling with relaxed loads and one acquire fence at the end was measured slower: +0.4 us per stage)
         unsigned got;
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(sync) : "memory");
         } while ((int)(got - want) < 0);
-        if (cta == 0 && s == s_begin + 1)       // every CTA has read `base`: publish the next launch's base
-          *reinterpret_cast<volatile unsigned*>(sync + 1) = base + (unsigned)(s_end - s_begin - 1) * (unsigned)ncta;
+        if (cta == 0 && nbar == 1)              // every CTA has read `base`: publish the next launch's base
+          *reinterpret_cast<volatile unsigned*>(sync + 1) = base + (unsigned)nbar_total * (unsigned)ncta;
       }
       d_consumer_sync();
     }
@@ -416,7 +435,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       const __half* xg = S->x;
       // o_proj's gather (qlinear.py:275): copy x to shared memory first (coalesced, one L2 round trip; the buffer aliases
       // the partial-sum slices, idle between two stages), then gather from there instead of 16 scattered 2-byte L2 loads
-      const bool xraw_ok = S->gather != nullptr && (size_t)M * (size_t)K * 2 <= (size_t)L.part_bytes;
+      const bool xraw_ok = S->gather != nullptr && !ll_x && (size_t)M * (size_t)K * 2 <= (size_t)L.part_bytes;
       const uint32_t xraw = d_smem_u32(dsm + L.part);
       if (xraw_ok) {
         for (int i = tid; i < M * (K >> 3); i += kDThreads) {
@@ -425,7 +444,21 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         }
         d_consumer_sync();
       }
+      // data-flow input: x is read from the 8-byte words {two fp16 values, epoch} the producing stage stores, each load
+      // repeated until the word carries this run's epoch (no barrier, no fence: the word is its own flag)
+      const uint2* xll = ll_x ? S->x_ll : nullptr;
+      auto ll_word = [&](const uint2* base_ll, size_t idx) -> uint32_t {
+        uint2 w;
+        do {
+          asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(base_ll + idx) : "memory");
+        } while (w.y != epoch);
+        return w.x;
+      };
       auto ldx16 = [&](const __half* row, int b, int col) -> unsigned short {
+        if (xll) {
+          const uint32_t w = ll_word(xll, ((size_t)b * K + col) >> 1);
+          return (unsigned short)((col & 1) ? (w >> 16) : (w & 0xffffu));
+        }
         if (xraw_ok) {
           unsigned short r16;
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16) : "r"(xraw + (uint32_t)((b * K + col) * 2)) : "memory");
@@ -455,6 +488,18 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             auto pk = [&](int a, int c) { return (uint32_t)ldx16(xr, b, a) | ((uint32_t)ldx16(xr, b, c) << 16); };
             v0 = make_uint4(pk(i0.x, i0.y), pk(i0.z, i0.w), pk(i1.x, i1.y), pk(i1.z, i1.w));
             v1 = make_uint4(pk(i2.x, i2.y), pk(i2.z, i2.w), pk(i3.x, i3.y), pk(i3.z, i3.w));
+          } else if (xll) {
+            // 8 + 8 values = 4 + 4 words: all loads first (one round trip when the data is there), then re-poll stragglers
+            const uint2* p0 = xll + (((size_t)b * K + k0) >> 1);
+            uint2 w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w[j].x), "=r"(w[j].y) : "l"(p0 + (j < 4 ? j : j + 4)) : "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (w[j].y != epoch) w[j].x = ll_word(p0, (size_t)(j < 4 ? j : j + 4));
+            v0 = make_uint4(w[0].x, w[1].x, w[2].x, w[3].x);
+            v1 = make_uint4(w[4].x, w[5].x, w[6].x, w[7].x);
           } else {
             v0 = d_ldcg128(xr + k0);
             v1 = d_ldcg128(xr + k0 + 16);
@@ -477,6 +522,9 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           const int4 a = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj)), c = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj + 4));
           auto pk = [&](int i0, int i1) { return (uint32_t)ldx16(xr, b, i0) | ((uint32_t)ldx16(xr, b, i1) << 16); };
           xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
+        } else if (xll) {
+          const size_t i0 = ((size_t)b * K + K - r + 8 * jj) >> 1;
+          xo_v = make_uint4(ll_word(xll, i0), ll_word(xll, i0 + 1), ll_word(xll, i0 + 2), ll_word(xll, i0 + 3));
         } else {
           xo_v = d_ldcg128(xr + K - r + 8 * jj);
         }
@@ -559,19 +607,19 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             const int bits = __float_as_int(fmaf(v, sc, 12582912.f));
             return (uint32_t)(bits + (0x00808080 - 0x4B400000)) ^ 0x00808080u;
           };
-          uint32_t dg[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { dg[2 * j] = digits(f[j].x); dg[2 * j + 1] = digits(f[j].y); }
+
           // Word c of digit column d = bytes {first[2c], second[2c], first[2c+1], second[2c+1]} (first = k0 + ., second =
           // k0 + 16 + .): the B-fragment register of lane t = c for this item's 32-column chunk tt = 2 T + h and nibble
           // position hs.  Lane t's 16-byte row of (hs, column) holds its four chunks' words, index tt.
           const uint32_t dst = xdig + (uint32_t)st * XSTEP + (uint32_t)hs * XHALF + (uint32_t)(4 * b) * 64 + (uint32_t)tt * 4;
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const uint32_t sel = 0x0040u + 0x11u * (uint32_t)d;
+          for (int c = 0; c < 4; ++c) {
+            // (f[c] = first[2c], first[2c+1]; f[4 + c] = second[2c], second[2c+1]: four digit words live at a time)
+            const uint32_t da = digits(f[c].x), db = digits(f[4 + c].x), dc = digits(f[c].y), dd = digits(f[4 + c].y);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t ww = d_prmt(d_prmt(dg[2 * c], dg[8 + 2 * c], sel), d_prmt(dg[2 * c + 1], dg[8 + 2 * c + 1], sel), 0x5410u);
+            for (int d = 0; d < 3; ++d) {
+              const uint32_t sel = 0x0040u + 0x11u * (uint32_t)d;
+              const uint32_t ww = d_prmt(d_prmt(da, db, sel), d_prmt(dc, dd, sel), 0x5410u);
               asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + (uint32_t)(d * 64 + c * 16)), "r"(ww) : "memory");
             }
           }
@@ -603,6 +651,12 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       d_consumer_sync();
     }
 
+    // the next stage's descriptor, into the other buffer: every warp is past its last read of the stage before this one,
+    // and the copy lands long before the post-consume barrier after which the next stage reads it
+    static_assert(sizeof(DecStage) % 16 == 0, "the descriptor is copied in 16-byte pieces");
+    if (s + 1 < s_end && tid >= 32 && tid < 32 + (int)(sizeof(DecStage) / 16))
+      d_cp16p(d_smem_u32(reinterpret_cast<uint8_t*>(ccache2) + ((s + 1 - s_begin) & 1) * 512) + (uint32_t)(tid - 32) * 16,
+              reinterpret_cast<const uint8_t*>(stages + s + 1) + (size_t)(tid - 32) * 16);
     dec_stamp(L, s, 1);
     // ---- the tile-blocks of the stage -------------------------------------------------------------------------
     {
@@ -634,6 +688,8 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           const uint32_t sbase = ring + (uint32_t)cslot * (uint32_t)L.slot;
           // wait for the block (lane 0 polls, so that the loop is warp-uniform); meanwhile help refilling free slots
           const long long tw0 = dbg ? clock64() : 0;
+          if (dbg && dbg_prev) dbg_fill += tw0 - dbg_prev;   // (block-to-block period inside a stage)
+          dbg_prev = tw0;
           const bool ready0 = dbg ? d_mbar_test(bars + 8 * cslot, cpar) : true;
           d_mbar_wait(bars + 8 * cslot, cpar);               // the block's bytes have landed (every lane acquires them)
           const long long tw1 = dbg ? clock64() : 0;
@@ -721,6 +777,8 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         }
       }
     }
+    dbg_prev = 0;
+    asm volatile("cp.async.wait_all;" ::: "memory");        // (the next stage's descriptor)
     d_consumer_sync();
     dec_stamp(L, s, 2);
 
@@ -728,11 +786,13 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     {
       const int epi = S->epilogue;
       const int nitems = R.ntiles * 16 * M;
-      for (int i = tid; i < nitems; i += kDThreads) {
+      const uint2* rll = (LL && S->res_ll != nullptr && S->res_src >= s_begin) ? S->res_ll : nullptr;
+      for (int i0 = warp * 32; i0 < nitems; i0 += kDThreads) {          // whole warps: the pair exchange below is a shuffle
+        const int i = i0 + lane;
         const int b = i % M, rr = (i / M) & 15, j = i / (16 * M);
         const int qi = 4 * j + (rr >> 2);
-        if (qi >= R.nq) continue;
-        if (epi == QEFT_EPI_SWIGLU && (rr & 4)) continue;          // up rows are consumed by their gate rows
+        // (SwiGLU: up rows are consumed by their gate rows)
+        const bool valid = i < nitems && qi < R.nq && !(epi == QEFT_EPI_SWIGLU && (rr & 4));
         auto tile_sum = [&](int row) {
           const float* src = part + (size_t)(j * kDWarps * M + b) * 16 + row;
           float a = 0.f;
@@ -740,39 +800,62 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           for (int w = 0; w < kDWarps; ++w) a += src[w * M * 16];
           return a;
         };
-        int pi, lq;
-        dec_locate(S, R.qa + qi, pi, lq);
-        const DecPart& P = S->part[pi];
-        const int n = 4 * lq + (rr & 3);
-        float a = tile_sum(rr);
-        if (P.bias) a += __half2float(P.bias[n]);
-        __half h = __float2half_rn(a);
-        if (epi == QEFT_EPI_SWIGLU) {
-          // silu(gate) * up, both rounded to fp16 first like the unfused linears (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x))
-          const DecPart& Pu = S->part[1];
-          float u = tile_sum(rr + 4);
-          if (Pu.bias) u += __half2float(Pu.bias[n]);
-          const float gf = __half2float(h);
-          const __half sg = __float2half_rn(gf / (1.f + __expf(-gf)));
-          h = __hmul(sg, __float2half_rn(u));
-        } else if (S->residual) {
-          const __half res = __ushort_as_half(d_ldcg16(S->residual + (size_t)b * P.N + n));
-          h = __hadd(res, h);
+        __half h = __float2half_rn(0.f);
+        int n = 0;
+        const DecPart* Pp = &S->part[0];
+        if (valid) {
+          int pi, lq;
+          dec_locate(S, R.qa + qi, pi, lq);
+          Pp = &S->part[pi];
+          n = 4 * lq + (rr & 3);
+          float a = tile_sum(rr);
+          if (Pp->bias) a += __half2float(Pp->bias[n]);
+          h = __float2half_rn(a);
+          if (epi == QEFT_EPI_SWIGLU) {
+            // silu(gate) * up, both rounded to fp16 first like the unfused linears (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x))
+            const DecPart& Pu = S->part[1];
+            float u = tile_sum(rr + 4);
+            if (Pu.bias) u += __half2float(Pu.bias[n]);
+            const float gf = __half2float(h);
+            const __half sg = __float2half_rn(gf / (1.f + __expf(-gf)));
+            h = __hmul(sg, __float2half_rn(u));
+          } else if (S->residual) {
+            __half res;
+            if (rll) {
+              // the residual was produced in this launch: read it from its data-flow words
+              uint2 w;
+              do {
+                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y)
+                             : "l"(rll + (((size_t)b * Pp->N + n) >> 1)) : "memory");
+              } while (w.y != epoch);
+              res = __ushort_as_half((unsigned short)((n & 1) ? (w.x >> 16) : (w.x & 0xffffu)));
+            } else {
+              res = __ushort_as_half(d_ldcg16(S->residual + (size_t)b * Pp->N + n));
+            }
+            h = __hadd(res, h);
+          }
+          Pp->y[(size_t)b * Pp->N + n] = h;
         }
-        P.y[(size_t)b * P.N + n] = h;
+        // data-flow copy for the stages of this launch that read y: rows n (even) and n + 1 sit M lanes apart
+        const unsigned hb = (unsigned)__half_as_ushort(h);
+        const unsigned hn = LL ? __shfl_down_sync(0xffffffffu, hb, M) : 0u;
+        if (LL && valid && !(n & 1) && uses_ll && Pp->y_ll != nullptr && Pp->ll_consumer < s_end) {
+          uint2 w = make_uint2(hb | (hn << 16), epoch);
+          asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(Pp->y_ll + (((size_t)b * Pp->N + n) >> 1)), "r"(w.x), "r"(w.y) : "memory");
+        }
       }
     }
-    if (s + 1 < s_end) {
-      // (one signal per CTA: one signal per warp was measured slower -- 16 x 148 atomics on one address per stage)
+    if (s + 1 < s_end && !(LL && S->nx_ll && S->nx_src >= s_begin)) {
+      // the next stage waits at a barrier (one signal per CTA: one signal per warp was measured slower -- 16 x 148
+      // atomics on one address per stage)
       d_consumer_sync();
       if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
-      // the next stage's descriptor, into the other buffer (its L2 round trip overlaps the wait at the barrier)
-      if (tid >= 32 && tid < 32 + kStageWords)
-        reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ccache2) + ((s + 1 - s_begin) & 1) * 384)[tid - 32] =
-            reinterpret_cast<const uint32_t*>(stages + s + 1)[tid - 32];
     }
     dec_stamp(L, s, 3);
   }
+  // the run's epoch becomes the base of the next run's (every CTA read it at its start: this CTA could only get here
+  // after consuming words of all the others)
+  if (LL && uses_ll && cta == 0 && tid == 0) *reinterpret_cast<volatile unsigned*>(sync + 2) = epoch;
   if (dbg && lane == 0) {
     unsigned long long* o = L.stamps + (size_t)(s_end - s_begin) * 32 + (warp == 0 ? 0 : 8);
     o[0] = (unsigned long long)dbg_wait; o[1] = (unsigned long long)dbg_math; o[2] = 0;
@@ -798,9 +881,10 @@ static int dec_env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int M>
-static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, size_t smem, int grid, cudaStream_t stream) {
-  auto kern = decode_w4_kernel<M>;
+template <int M, bool LL>
+static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, size_t smem, int grid, cudaStream_t stream,
+                      int nbar_total, int uses_ll) {
+  auto kern = decode_w4_kernel<M, LL>;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -818,9 +902,9 @@ static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, s
   attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: they wait for one another at stage boundaries
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (s1 - s0 > 1) ? 1 : 0;
+  cfg.numAttrs = (s1 - s0 > 1) ? 1 : 0;        // (barriers or data-flow polling between stages: CTAs wait for one another)
   const DecStage* st = p->d_stages;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L, nbar_total, uses_ll);
   if (e != cudaSuccess) return (int)e;
   count_launch();
   return QEFT_OK;
@@ -869,6 +953,8 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
       dp.ow = r > 0 ? static_cast<const __half*>(a.oweight) : static_cast<const __half*>(a.scales);
       dp.bias = static_cast<const __half*>(a.bias);
       dp.y = static_cast<__half*>(a.y);
+      dp.y_ll = nullptr;
+      dp.ll_consumer = 1 << 30;
       dp.side = nullptr;
       dp.side_q = cdiv(K - r, 128) * 16 + 8 * r;
       dp.N = a.N;
@@ -890,6 +976,56 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
     d.nou = r / 32;
     d.total_q = total_q;
     d.epilogue = q.epilogue;
+  }
+  // Data-flow links: a stage whose x (or residual) IS the y of an earlier stage's projection reads it from that
+  // projection's data-flow words (allocated here, owned by the program) instead of waiting at a barrier.
+  const int ll_env = dec_env_int("QEFT_DECODE_LL", 0);      // (read at every creation: tests build both kinds of program)
+  for (int s = 0; s < nstages; ++s) {
+    DecStage& d = p->h_stages[s];
+    d.x_ll = nullptr; d.res_ll = nullptr; d.x_src = -1; d.res_src = -1; d.force_barrier = 0; d.nx_ll = 0; d.nx_src = -1;
+  }
+  auto link = [&](const void* ptr, int width, int s, const uint2*& out_ll, int& out_src) -> int {
+    // the latest earlier stage with a projection whose output buffer is exactly `ptr` ([m, width])
+    for (int ps = s - 1; ps >= 0; --ps) {
+      DecStage& pd = p->h_stages[ps];
+      const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
+      for (int i = 0; i < nout; ++i) {
+        DecPart& pp = pd.part[i];
+        if (pp.y != ptr) continue;
+        if (pp.N != width || (width & 1)) return -1;            // produced in the program, but not linkable: barrier
+        if (!pp.y_ll) {
+          void* buf = nullptr;
+          if (cudaMalloc(&buf, (size_t)m * pp.N * 4) != cudaSuccess) return -2;
+          cudaMemset(buf, 0, (size_t)m * pp.N * 4);
+          p->side_tables.push_back(buf);
+          pp.y_ll = static_cast<uint2*>(buf);
+        }
+        if (s < pp.ll_consumer) pp.ll_consumer = s;
+        out_ll = pp.y_ll;
+        out_src = ps;
+        return 1;
+      }
+    }
+    return 0;                                                   // not produced by this program: external input
+  };
+  if (ll_env) {
+    for (int s = 1; s < nstages; ++s) {
+      DecStage& d = p->h_stages[s];
+      const int rx = link(d.x, d.K, s, d.x_ll, d.x_src);
+      int rr = 0;
+      if (d.residual) rr = link(d.residual, d.part[0].N, s, d.res_ll, d.res_src);
+      if (rx == -2 || rr == -2) {
+        for (void* b : p->side_tables) cudaFree(b);
+        delete p;
+        return (int)cudaErrorMemoryAllocation;
+      }
+      if (rx < 0 || rr < 0) d.force_barrier = 1;
+    }
+    for (int s = 0; s + 1 < nstages; ++s) {
+      const DecStage& nx = p->h_stages[s + 1];
+      p->h_stages[s].nx_ll = (nx.x_ll != nullptr && !nx.force_barrier) ? 1 : 0;
+      p->h_stages[s].nx_src = nx.x_src;
+    }
   }
   // the decode side tables (see dec_build_side_kernel): one per projection, owned by the program
   for (int s = 0; s < nstages; ++s) {
@@ -988,7 +1124,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   const size_t xsum = (size_t)max_steps * 16 + 16;
   const size_t xo = (size_t)m * max_r * 2 + 16;
   const size_t part = (size_t)max_tiles * kDWarps * m * 16 * sizeof(float);
-  const size_t misc = 2560;
+  const size_t misc = 3072;
   const size_t fixed = ((xdig + 127) & ~(size_t)127) + ((xsum + 127) & ~(size_t)127) + ((xo + 127) & ~(size_t)127) +
                        ((part + 127) & ~(size_t)127) + misc;
   if (fixed + 2 * (size_t)L.slot > kDSmemMax) return QEFT_E_UNSUPPORTED;
@@ -1014,5 +1150,18 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   }
   L.stamps = p->d_stamps;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-return m == 1 ? dec_launch<1>(p, stage_begin, stage_end, L, off, grid, st) : dec_launch<2>(p, stage_begin, stage_end, L, off, grid, st);
+// which stages of the range wait at a barrier, and whether any reads data-flow words written in this launch
+  int nbar_total = 0, uses_ll = 0;
+  for (int s = stage_begin + 1; s < stage_end; ++s) {
+    const DecStage& d = p->h_stages[s];
+    const bool ll = d.x_ll != nullptr && d.x_src >= stage_begin && !d.force_barrier;
+    nbar_total += ll ? 0 : 1;
+    uses_ll |= ll ? 1 : 0;
+    if (d.res_ll != nullptr && d.res_src >= stage_begin) uses_ll = 1;
+  }
+  if (uses_ll)
+    return m == 1 ? dec_launch<1, true>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll)
+                  : dec_launch<2, true>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll);
+  return m == 1 ? dec_launch<1, false>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll)
+                : dec_launch<2, false>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll);
 }

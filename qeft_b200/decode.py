@@ -100,6 +100,58 @@ class PackedDecoderStack:
         self.program = qeft_cuda.DecodeProgram(stages, m=self.batch)
         return self.program
 
+    def enable_chain_program(self, dataflow=False, eps=1e-5):
+        """The token as ONE launch in which the stages really feed each other, with a Llama block's elementwise glue
+        fused in: per block [RMSNorm -> q|k|v], [o_proj (reorder gather) + residual], [RMSNorm -> gate|up ->
+        SiLU*mul], [down_proj + residual]; the next block's q|k|v reads this block's output.  Attention is not part of
+        the path: o_proj consumes the q projection in its place.  ``dataflow``: stages are ordered by the data-flow words
+        of their inputs (no barrier); False (default, measured faster: 1.47 vs 2.30 ms per 7B token, profiles/r02_decode_chain_*):
+        by gpu-scope barriers (``QEFT_DECODE_LL=0``).  Same weights and weight bytes
+        as :meth:`enable_program`."""
+        import os
+        assert self.world == 1 and self.fused and self.kv == self.h
+        m, dev = self.batch, self.device
+        g = torch.Generator(device=dev)
+        g.manual_seed(4242)
+        self.ln = [(1 + 0.1 * torch.randn((2, self.h), device=dev, generator=g)).half() for _ in self.blocks]
+        self.chain = []
+        stages = []
+        hidden = self.x_h
+
+        def parts(blk, names, ys):
+            return [{"qweight": blk[n]["qweight"], "scales": blk[n]["scales"], "scaled_zeros": blk[n]["scaled_zeros"],
+                     "oweight": blk[n].get("oweight"), "bias": blk[n].get("bias"), "N": blk[n]["N"], "y": y}
+                    for n, y in zip(names, ys)]
+
+        for li, blk in enumerate(self.blocks):
+            e = lambda n: torch.empty((m, n), dtype=torch.float16, device=dev)  # noqa: E731
+            buf = {"q": e(self.h), "k": e(self.kv), "v": e(self.kv), "h2": e(self.h), "act": e(self.f), "up": e(self.f),
+                   "out": e(self.h)}
+            kw = {"K": self.h, "r": self.r, "G": self.G}
+            stages.append({"x": hidden, **kw, "norm_weight": self.ln[li][0], "norm_eps": eps,
+                           "parts": parts(blk, ("q", "k", "v"), (buf["q"], buf["k"], buf["v"]))})
+            st = {"x": buf["q"], **kw, "epilogue": "residual", "residual": hidden, "parts": parts(blk, ("o",), (buf["h2"],))}
+            if self.r > 0:
+                st["x_gather"] = blk["o"]["reorder_ids32"]
+            stages.append(st)
+            stages.append({"x": buf["h2"], **kw, "norm_weight": self.ln[li][1], "norm_eps": eps, "epilogue": "swiglu",
+                           "parts": parts(blk, ("gate", "up"), (buf["act"], buf["up"]))})
+            stages.append({"x": buf["act"], "K": self.f, "r": self.r, "G": self.G, "epilogue": "residual",
+                           "residual": buf["h2"], "parts": parts(blk, ("down",), (buf["out"],))})
+            self.chain.append(buf)
+            hidden = buf["out"]
+        old = os.environ.get("QEFT_DECODE_LL")
+        os.environ["QEFT_DECODE_LL"] = "1" if dataflow else "0"
+        try:
+            self.program = qeft_cuda.DecodeProgram(stages, m=self.batch)
+        finally:
+            if old is None:
+                del os.environ["QEFT_DECODE_LL"]
+            else:
+                os.environ["QEFT_DECODE_LL"] = old
+        self.chain_mode = "dataflow" if dataflow else "barrier"
+        return self.program
+
     def enable_allgather(self, process_group):
         """Column-sharded execution: after each launch group, all-gather the ranks' output slices (NCCL over
         NVLink).  The gathered buffer is [world, group_width]: rank-major, then q|k|v (or gate|up) inside."""
@@ -212,6 +264,8 @@ class PackedDecoderStack:
 
     def result(self):
         """The tensor a step produces: the last projection's output (the GATHERED [1, N] row when sharded)."""
+        if getattr(self, "chain", None) and self.program is not None:
+            return self.chain[-1]["out"]
         if getattr(self, "fused_gather", None) is not None:
             return self.fused_gather[-1][-1][1]
         if self.pg is not None:

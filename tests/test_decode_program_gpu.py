@@ -350,3 +350,50 @@ def test_fused_decoder_block_minus_attention(m):
     assert_close(got_act, act, "swiglu", atol_rms=1.5e-2)
     out = (got_h2.astype(np.float32) + ref_forward(Ls["down"], got_act).astype(np.float32)).astype(np.float16)
     assert_close(y_out[0].cpu().numpy(), out, "h2 + down_proj(act)")
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_llama7b_chain_dataflow_equals_barrier_program(batch):
+    """The fused decoder chain (RMSNorm / SiLU*mul / residual glue, stages feeding each other) at Llama-2-7B shapes, 3
+    blocks: ordering the stages by the data-flow words of their inputs gives bit-identical results to ordering them by
+    gpu-scope barriers, run after run and under CUDA-graph replay; sub-ranges fall back to plain inputs."""
+    from qeft_b200.decode import PackedDecoderStack
+    outs = {}
+    for mode in (True, False):
+        st = PackedDecoderStack("7b", layers=3, fast_synth=True, batch=batch, seed=3)
+        prog = st.enable_chain_program(dataflow=mode)
+        prog.run()
+        torch.cuda.synchronize()
+        first = [{k: v.clone() for k, v in b.items() if k != "up"} for b in st.chain]
+        for b in st.chain:
+            for v in b.values():
+                v.fill_(float("nan"))
+        prog.run()
+        prog.run(0, 5)
+        prog.run(5, 12)                                   # block boundaries inside and outside the sub-ranges
+        torch.cuda.synchronize()
+        for a, b in zip(first, st.chain):
+            for k in a:
+                assert torch.isfinite(b[k].float()).all(), (mode, k)
+                assert torch.equal(a[k].view(torch.int16), b[k].view(torch.int16)), (mode, k)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            prog.run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            prog.run()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(first, st.chain):
+            for k in a:
+                assert torch.equal(a[k].view(torch.int16), b[k].view(torch.int16)), (mode, "graph", k)
+        outs[mode] = first
+        del st, prog, g
+        torch.cuda.empty_cache()
+    for a, b in zip(outs[True], outs[False]):
+        for k in a:
+            assert torch.equal(a[k].view(torch.int16), b[k].view(torch.int16)), k

@@ -53,7 +53,7 @@ def main():
                             "cycles_per_block": round(float(extra[16]) / max(1, int(extra[17])), 1)}
     for nm, e in (("warp0", extra[:8]), ("warp15", extra[8:16])):
         out["cta0_" + nm] = {"wait_cycles": int(e[0]), "math_cycles": int(e[1]), "issue_cycles": int(e[2]),
-                             "fill_latency_cycles_when_waited": int(e[3]), "issues": int(e[4]), "blocks_waited": int(e[5]),
+                             "block_period_cycles_sum": int(e[3]), "issues": int(e[4]), "blocks_waited": int(e[5]),
                              "blocks": int(e[6])}
     print(json.dumps(out))
 
