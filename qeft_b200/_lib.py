@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libqeft_b200.so")
+# (QEFT_B200_LIB: development switch, an alternative build of the same library for A/B timing -- tools/build_variant.sh)
+LIB_PATH = os.environ.get("QEFT_B200_LIB") or os.path.join(_HERE, "csrc", "libqeft_b200.so")
 
 OK = 0
 E_UNSUPPORTED = -6

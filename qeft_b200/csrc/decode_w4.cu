@@ -33,6 +33,7 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 namespace qeft {
@@ -59,8 +60,8 @@ struct DecPart {
   const __half* ow;       // plain [N, r]
   const __half* bias;
   __half* y;              // [m, N]
-  uint2* y_ll;            // data-flow copy of y or null: [m * N / 2] words {two fp16 results, epoch of the run}
-  int ll_consumer;        // first stage that reads y_ll (the words are written only when that stage is part of the launch)
+  const void* y_ll;       // non-null: a later stage of the program reads y by data-flow (polls it: see the kernel's header)
+  int ll_consumer;        // first stage that does
   int pad1;
   const uint8_t* side;    // decode side table (built at program creation), per qweight row: [steps][scales of its 4 rows |
                           // scaled zeros of its 4 rows] then the fp16 outlier columns in MMA-fragment order
@@ -100,10 +101,10 @@ struct DecStage {
   const int32_t* gather;      // [K] or null: x[:, gather[k]] is column k
   const __half* norm_w;       // [K] or null: RMSNorm weight applied to x on the way in
   const __half* residual;     // [m, N] or null: added to the (fp16-rounded) result of part 0
-  const uint2* x_ll;          // data-flow copy of x (the y_ll of the stage that produces it) or null
-  const uint2* res_ll;        // the same for the residual
-  int x_src, res_src;         // producing stages (the copies are valid only when those ran in THIS launch)
-  int force_barrier;          // a dependency on an earlier stage that is not linked by data-flow words
+  const void* x_ll;           // non-null: x is the y of an earlier stage of the program and may be read by data-flow
+  const void* res_ll;         // the same for the residual
+  int x_src, res_src;         // producing stages (data-flow applies only when those run in THIS launch)
+  int force_barrier;          // a dependency on an earlier stage that cannot be read by data-flow
   int nx_ll, nx_src;          // x_ll != null && !force_barrier / x_src of the NEXT stage (whether it waits at a barrier)
   float norm_eps;
   int nparts;
@@ -114,16 +115,27 @@ struct DecStage {
   int epilogue;               // QEFT_EPI_*
 };
 
+// Data-flow outputs are re-armed at the start of every launch: one entry per projection whose y a later stage polls.
+struct DecReset { unsigned short* y; int n; int prod, cons; int pad; };   // [m x N] halves, producing / first consuming stage
+
 struct DecLayout {            // shared-memory carve-up (bytes from the start of dynamic shared memory)
   int nslots, slot;           // ring at offset 0: nslots slots of `slot` bytes: [4 x kQArea packed words][4 x sarea side bytes]
   int slot_s, sarea;
   int xdig, xdig_bytes, xsum, xo, part, part_bytes, misc;
+  int poll_ns;                // back-off between two polls of a data-flow input (QEFT_DECODE_POLL_NS)
   int debug;                  // QEFT_DECODE_DEBUG bit mask (bisecting switches; results are WRONG when set)
   unsigned long long* stamps; // debug (QEFT_DECODE_STAMPS): [stage][4 CTAs][8] globaltimer values, or null
+  unsigned long long* stamps_all;   // debug: [stage][160 CTAs][4]: stage entered, x staged, blocks consumed, rows stored
 };
 
+template <bool DBG>
 __device__ __forceinline__ void dec_stamp(const DecLayout& L, int s, int i) {
-  if (L.stamps && threadIdx.x == 0) {
+  if (DBG && L.stamps_all && threadIdx.x == 0 && i < 4 && blockIdx.x < 160) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    L.stamps_all[((size_t)s * 160 + blockIdx.x) * 4 + i] = t;
+  }
+  if (DBG && L.stamps && threadIdx.x == 0) {
     const int c = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : (blockIdx.x == gridDim.x / 2 ? 2 : (blockIdx.x == 1 ? 3 : -1)));
     if (c >= 0) {
       unsigned long long t;
@@ -183,6 +195,51 @@ __device__ __forceinline__ unsigned short d_ldcg16(const void* p) {
   asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
   return r;
 }
+// ---- data-flow by sentinel ---------------------------------------------------------------------------------------
+// A y that a later stage of the same launch reads is its own "ready" flag: the launch first overwrites it with the fp16
+// bit pattern 0xFFFF (a NaN no result ever has: results that are NaN are stored as 0x7E00), the producing CTAs store
+// plain results, and a consumer re-reads any 16-byte piece in which an 0xFFFF is left.  No fence, no counter, no second
+// copy of the data: a value is usable the moment it is visible, and every fp16 element is its own flag, so no ordering
+// between different elements is needed (relaxed gpu-scope accesses).
+constexpr unsigned kDfEmpty = 0xFFFFu;
+__device__ __forceinline__ bool d_has_empty(const uint4& v) {
+  return (__vcmpeq2(v.x, 0xFFFFFFFFu) | __vcmpeq2(v.y, 0xFFFFFFFFu) | __vcmpeq2(v.z, 0xFFFFFFFFu) | __vcmpeq2(v.w, 0xFFFFFFFFu)) != 0u;
+}
+__device__ __forceinline__ uint4 d_ldrelaxed128(const void* p) {
+  uint4 r;
+#ifdef QEFT_DEC_POLL_CG
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#else
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#endif
+  return r;
+}
+__device__ __forceinline__ unsigned short d_ldrelaxed16(const void* p) {
+  unsigned short r;
+  asm volatile("ld.relaxed.gpu.global.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void d_strelaxed16(void* p, unsigned short v) {
+#ifdef QEFT_DEC_POLL_CG
+  *reinterpret_cast<volatile unsigned short*>(p) = v;
+#else
+  asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
+#endif
+}
+// 16 bytes of x: polled until every element has arrived when the producer runs in this launch
+__device__ __forceinline__ uint4 d_ldx128(const void* p, bool poll, unsigned ns) {
+  if (!poll) return d_ldcg128(p);
+  uint4 v = d_ldrelaxed128(p);
+  while (d_has_empty(v)) { __nanosleep(ns); v = d_ldrelaxed128(p); }
+  return v;
+}
+__device__ __forceinline__ unsigned short d_ldx16(const void* p, bool poll, unsigned ns) {
+  if (!poll) return d_ldcg16(p);
+  unsigned short v = d_ldrelaxed16(p);
+  while (v == kDfEmpty) { __nanosleep(ns); v = d_ldrelaxed16(p); }
+  return v;
+}
+
 __device__ __forceinline__ void d_imma(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                        uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -270,10 +327,12 @@ __device__ __forceinline__ DecTiles dec_tiles(const DecStage* S, int cta, int nc
 // the block nslots ahead in the sequence -- which may belong to a later stage: the stream does not stop at a stage
 // boundary, ~150 KB per SM stay in flight while the CTAs meet at the barrier and convert the next x.
 // LL: the launch uses data-flow words (stages ordered by polling their inputs); false compiles every such path out.
-template <int M, bool LL>
+// DBG: the instrumented build of the kernel (QEFT_DECODE_STAMPS / QEFT_DECODE_DEBUG): in-kernel timers and the bisecting
+// switches; compiled out of the shipping instances (they cost ~10 % of the consumers' issue slots when merely predicated).
+template <int M, bool LL, bool DBG>
 __global__ void __maxnreg__(QEFT_DEC_MAXREG)
 decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, unsigned* sync, const DecLayout L,
-                 int nbar_total, int uses_ll) {
+                 int nbar_total, int uses_ll, const DecReset* __restrict__ resets, int nresets) {
   extern __shared__ __align__(128) uint8_t dsm[];
   constexpr int NCOLS = 4 * M;
   constexpr uint32_t XSTEP = 128u * NCOLS;                   // digit bytes per 128-column step: [2 nibble halves][NCOLS][4 t][16 B]
@@ -282,6 +341,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const int g = lane >> 2, t = lane & 3;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int NS = L.nslots;
+  const unsigned pns = (unsigned)L.poll_ns;
 
   const uint32_t ring = d_smem_u32(dsm);
   const uint32_t xdig = d_smem_u32(dsm + L.xdig);
@@ -311,19 +371,18 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     reinterpret_cast<uint32_t*>(ccache2)[tid - 32] = reinterpret_cast<const uint32_t*>(stages + s_begin)[tid - 32];
   // the barrier counter only grows; `base` is its value when every CTA of this launch has started
   const unsigned base = *reinterpret_cast<volatile unsigned*>(sync + 1);
-  // data-flow words carry the epoch of the run that wrote them (sync[2] = epoch of the last run that used them)
-  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(sync + 2) + 1u;
   int nbar = 0;                                              // stage barriers passed so far
   __syncthreads();
 
-  // the fourth digit column of every batch row is never written: it must read as zero (its accumulator column is unused)
+  // (digit bytes of steps / columns a stage does not write read as zero)
   for (int i = tid; i < L.xdig_bytes / 16; i += kDBlock) d_sts128(xdig + (uint32_t)i * 16, 0u, 0u, 0u, 0u);
   __syncthreads();
 
   // debug counters (QEFT_DECODE_STAMPS): warp 0 and warp 15 of CTA 0 and the producer warp, clock64 cycles
   long long dbg_wait = 0, dbg_math = 0, dbg_issue = 0, dbg_fill = 0, dbg_prev = 0;
   int dbg_nissue = 0, dbg_nwaited = 0, dbg_nblocks = 0;
-  const bool dbg = L.stamps != nullptr && cta == 0 && (warp == 0 || warp >= kDWarps - 1);
+  const bool dbg = DBG && L.stamps != nullptr && cta == 0 && (warp == 0 || warp >= kDWarps - 1);
+  const int dbgsw = DBG ? L.debug : 0;                       // bisecting switches (results are wrong when set)
 
   // =================================== the producer warp ========================================================
   // Walks the CTA's tile-blocks through ALL stages of the launch and fills the ring: it only ever waits for a slot to
@@ -365,11 +424,11 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           // side bytes of the block: its steps' scales / scaled zeros and, on the tile's last block, the outlier columns
           // (they follow the last step's scales in the table, so it is one contiguous copy)
           const uint32_t sbytes = (uint32_t)(nsb * 16 + (kb == KB - 1 ? 8 * r : 0));
-          if (lane == 0) d_mbar_expect_tx(bar, (uint32_t)__popc(own4) * (((L.debug & 4) ? 0u : nbytes) + ((L.debug & 2) ? 0u : sbytes)));
+          if (lane == 0) d_mbar_expect_tx(bar, (uint32_t)__popc(own4) * (((dbgsw & 4) ? 0u : nbytes) + ((dbgsw & 2) ? 0u : sbytes)));
           __syncwarp();
           // rows this CTA does not own are NOT copied: their slot bytes are stale, their (independent) MMA rows are never stored
-          if (lane < 4 && own && !(L.debug & 4)) d_bulk_g2s(sbase + (uint32_t)(q * kQArea), wsrc + off, nbytes, bar);
-          if (lane < 4 && own && !(L.debug & 2))
+          if (lane < 4 && own && !(dbgsw & 4)) d_bulk_g2s(sbase + (uint32_t)(q * kQArea), wsrc + off, nbytes, bar);
+          if (lane < 4 && own && !(dbgsw & 2))
             d_bulk_g2s(sbase + (uint32_t)(L.slot_s + q * L.sarea), dsrc + (size_t)kb * (size_t)kSideSteps, sbytes, bar);
           if (++pslot == NS) { pslot = 0; ppar ^= 1u; }
           if (dbg) { dbg_issue += clock64() - t0; ++dbg_nissue; }
@@ -399,119 +458,122 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const uint32_t laneS = (uint32_t)(L.slot_s + (g >> 1) * L.sarea + (g & 1) * 4 + (zlane ? 8 : 0));
   const uint32_t laneO = (uint32_t)(L.slot_s + (g >> 1) * L.sarea + (g & 1) * 64 + t * 16);
   const uint32_t xdig_lane = xdig + (uint32_t)(g * 64 + t * 16);
+  // tile-end weights of this lane's two accumulator columns (four digit columns of a batch row weigh 256^i) and its
+  // 8 bytes in the warp's partial-sum slice [tile][warp][M][16 rows]
+  const float dc0 = (M == 1 ? (t == 0 ? 1.f : (t == 1 ? 65536.f : (t == 2 ? 1.f : 0.f))) : ((t & 1) ? 65536.f : 1.f));
+  const float dc1 = (M == 1 ? (t == 0 ? 256.f : (t == 1 ? 16777216.f : 0.f)) : ((t & 1) ? 16777216.f : 256.f));
+  const uint32_t part_w = d_smem_u32(dsm + L.part) + (uint32_t)(warp * M * 64 + g * 8);
+
+  // grid barrier of the consumer warps: one release per CTA on a counter that only grows, one polling thread per CTA
+  // (one signal per warp was measured slower -- 16 x 148 atomics on one address per stage; polling with relaxed loads and
+  // one acquire fence at the end: +0.4 us per stage)
+  auto barrier_arrive = [&]() {
+    d_consumer_sync();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
+  };
+  auto barrier_wait = [&]() {
+    ++nbar;
+    if (tid == 0) {
+      const unsigned want = base + (unsigned)nbar * (unsigned)ncta;
+      unsigned got;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(sync) : "memory");
+      } while ((int)(got - want) < 0);
+      if (cta == 0 && nbar == 1)              // every CTA has read `base`: publish the next launch's base
+        *reinterpret_cast<volatile unsigned*>(sync + 1) = base + (unsigned)nbar_total * (unsigned)ncta;
+    }
+    d_consumer_sync();
+  };
+  if (LL && uses_ll) {
+    // re-arm the data-flow outputs of this launch (one list entry per thread, this CTA's share of its elements), then
+    // one grid barrier: nobody polls a buffer that still holds the previous run's results
+    for (int i = tid; i < nresets; i += kDThreads) {
+      const DecReset e = resets[i];
+      if (e.prod >= s_begin && e.prod < s_end && e.cons < s_end) {
+        const int i0 = (int)(((long long)e.n * cta) / ncta), i1 = (int)(((long long)e.n * (cta + 1)) / ncta);
+        for (int k = i0; k < i1; ++k) d_strelaxed16(e.y + k, (unsigned short)kDfEmpty);
+      }
+    }
+    barrier_arrive();
+    barrier_wait();
+  }
 
 #pragma unroll 1
   for (int s = s_begin; s < s_end; ++s) {
     const DecStage* S = reinterpret_cast<const DecStage*>(reinterpret_cast<const uint8_t*>(ccache2) + ((s - s_begin) & 1) * 512);
 
-    // x produced by an earlier stage of this launch and linked by data-flow words: the stage polls the words it reads,
+    // x produced by an earlier stage of this launch and readable by data-flow: the stage polls the elements it reads,
     // no barrier.  Every other stage after the first waits until all CTAs have stored their rows of the previous one.
     // (The descriptor copy of stage s was written before the previous stage's post-consume barrier.)
     const bool ll_x = LL && S->x_ll != nullptr && S->x_src >= s_begin && !S->force_barrier;
-    if (s > s_begin && !ll_x) {
-      ++nbar;
-      if (tid == 0) {
-        const unsigned want = base + (unsigned)nbar * (unsigned)ncta;
-        // (polling with relaxed loads and one acquire fence at the end was measured slower: +0.4 us per stage)
-        unsigned got;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(sync) : "memory");
-        } while ((int)(got - want) < 0);
-        if (cta == 0 && nbar == 1)              // every CTA has read `base`: publish the next launch's base
-          *reinterpret_cast<volatile unsigned*>(sync + 1) = base + (unsigned)nbar_total * (unsigned)ncta;
-      }
-      d_consumer_sync();
-    }
+    if (s > s_begin && !ll_x) barrier_wait();
     const DecTiles R = dec_tiles(S, cta, ncta);
     const int K = S->K, r = S->r, ns = S->nsteps;
 
-    dec_stamp(L, s, 0);
-    // ---- x: block fixed point per 128-column step, three signed-byte digits ------------------------------------------
-    //   x_k ~= X_k 2^(e-22),  X_k = d0 + 256 d1 + 65536 d2,  d_i in [-128, 127],  2^e > max |x| of the step
-    // (exact for every element within 12 binades of the step's maximum; fp16 has 11 significant bits).  One exponent per
+    dec_stamp<DBG>(L, s, 0);
+    // ---- x: block fixed point per 128-column step, signed-byte digits ------------------------------------------------
+    //   x_k ~= X_k 2^(e-22),  X_k = rint(x_k 2^(22-e)) a 23-bit integer,  2^e > max |x| of the step
+    // (exact for every element within 12 binades of the step's maximum; fp16 has 11 significant bits); what is stored are
+    // four base-256 digits d_i in [-128, 127] of 16 X_k (low-nibble columns) or X_k - 16 X_partner (high-nibble columns).
+    // One exponent per
     // STEP keeps the staging free of a CTA-wide reduction (the stage boundary's critical path: measured 0.8 us for the
     // first version's single exponent per row); the price is one multiply per row pair and step in the main loop.
     {
       const __half* xg = S->x;
       // o_proj's gather (qlinear.py:275): copy x to shared memory first (coalesced, one L2 round trip; the buffer aliases
       // the partial-sum slices, idle between two stages), then gather from there instead of 16 scattered 2-byte L2 loads
-      const bool xraw_ok = S->gather != nullptr && !ll_x && (size_t)M * (size_t)K * 2 <= (size_t)L.part_bytes;
+      const bool xraw_ok = S->gather != nullptr && (size_t)M * (size_t)K * 2 <= (size_t)L.part_bytes;
       const uint32_t xraw = d_smem_u32(dsm + L.part);
       if (xraw_ok) {
+        // (without a barrier in front of this stage, warps may still be adding the previous stage's slices)
+        if (ll_x) d_consumer_sync();
         for (int i = tid; i < M * (K >> 3); i += kDThreads) {
-          const uint4 v = d_ldcg128(xg + (size_t)i * 8);
+          const uint4 v = d_ldx128(xg + (size_t)i * 8, ll_x, pns);
           d_sts128(xraw + (uint32_t)i * 16, v.x, v.y, v.z, v.w);
         }
         d_consumer_sync();
       }
-      // data-flow input: x is read from the 8-byte words {two fp16 values, epoch} the producing stage stores, each load
-      // repeated until the word carries this run's epoch (no barrier, no fence: the word is its own flag)
-      const uint2* xll = ll_x ? S->x_ll : nullptr;
-      auto ll_word = [&](const uint2* base_ll, size_t idx) -> uint32_t {
-        uint2 w;
-        do {
-          asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(base_ll + idx) : "memory");
-        } while (w.y != epoch);
-        return w.x;
-      };
+      // data-flow input (ll_x): every load of x is repeated until the elements it covers have arrived (d_ldx128 / d_ldx16)
       auto ldx16 = [&](const __half* row, int b, int col) -> unsigned short {
-        if (xll) {
-          const uint32_t w = ll_word(xll, ((size_t)b * K + col) >> 1);
-          return (unsigned short)((col & 1) ? (w >> 16) : (w & 0xffffu));
-        }
         if (xraw_ok) {
           unsigned short r16;
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r16) : "r"(xraw + (uint32_t)((b * K + col) * 2)) : "memory");
           return r16;
         }
-        return d_ldcg16(row + col);
+        return d_ldx16(row + col, ll_x, pns);
       };
       const int32_t* gat = S->gather;
       const __half* nw = S->norm_w;
       const int live_k = S->nchunks * 32;
-      const int nitems = M * ns * 8;
+      const int nitems = M * ns * 16;
       const int npass = (nitems + kDThreads - 1) / kDThreads;
-      // item = (batch row b, step, chunk tt, hs): the 16 columns k0 .. k0+7 and k0+16 .. k0+23, k0 = 128 step + 32 tt + 8 hs;
-      // the 8 items of a step sit in 8 adjacent lanes, which agree on the step's sum and maximum by shuffles
-      auto load_item = [&](int it, uint4& v0, uint4& v1, int& b, int& st, bool& live) {
-        const int sb = it >> 3;
+      // item = (batch row b, step, sub): the 8 columns k0 .. k0+7, k0 = 128 step + 8 sub (one 16-byte load, lanes contiguous);
+      // sub = 4 tt + 2 half + hs: 32-column chunk tt, first / second 16 columns of the chunk, low / high nibble position.
+      // The 16 items of a step sit in 16 adjacent lanes, which agree on the step's sum and maximum by shuffles.
+      auto load_item = [&](int it, uint4& v0, int& b, int& st, bool& live) {
+        const int sb = it >> 4;
         b = sb / ns;
         st = sb - b * ns;
-        const int k0 = st * 128 + ((it >> 1) & 3) * 32 + (it & 1) * 8;
+        const int k0 = st * 128 + (it & 15) * 8;
         live = it < nitems && k0 < live_k;
-        v0 = v1 = make_uint4(0u, 0u, 0u, 0u);
+        v0 = make_uint4(0u, 0u, 0u, 0u);
         if (live) {
           const __half* xr = xg + (size_t)b * K;
           if (gat) {
             const int4 i0 = __ldg(reinterpret_cast<const int4*>(gat + k0)), i1 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 4));
-            const int4 i2 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 16)), i3 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 20));
             auto pk = [&](int a, int c) { return (uint32_t)ldx16(xr, b, a) | ((uint32_t)ldx16(xr, b, c) << 16); };
             v0 = make_uint4(pk(i0.x, i0.y), pk(i0.z, i0.w), pk(i1.x, i1.y), pk(i1.z, i1.w));
-            v1 = make_uint4(pk(i2.x, i2.y), pk(i2.z, i2.w), pk(i3.x, i3.y), pk(i3.z, i3.w));
-          } else if (xll) {
-            // 8 + 8 values = 4 + 4 words: all loads first (one round trip when the data is there), then re-poll stragglers
-            const uint2* p0 = xll + (((size_t)b * K + k0) >> 1);
-            uint2 w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w[j].x), "=r"(w[j].y) : "l"(p0 + (j < 4 ? j : j + 4)) : "memory");
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (w[j].y != epoch) w[j].x = ll_word(p0, (size_t)(j < 4 ? j : j + 4));
-            v0 = make_uint4(w[0].x, w[1].x, w[2].x, w[3].x);
-            v1 = make_uint4(w[4].x, w[5].x, w[6].x, w[7].x);
           } else {
-            v0 = d_ldcg128(xr + k0);
-            v1 = d_ldcg128(xr + k0 + 16);
+            v0 = d_ldx128(xr + k0, ll_x, pns);
           }
         }
       };
       // the loads of the first two passes and of the outlier activations are in flight together
-      uint4 k0a, k0b, k1a, k1b;
+      uint4 k0a, k1a;
       int kb0, kb1, ks0, ks1;
       bool kl0, kl1;
-      load_item(tid, k0a, k0b, kb0, ks0, kl0);
-      load_item(kDThreads + tid, k1a, k1b, kb1, ks1, kl1);
+      load_item(tid, k0a, kb0, ks0, kl0);
+      load_item(kDThreads + tid, k1a, kb1, ks1, kl1);
       const int nxo = M * (r >> 3);
       uint4 xo_v = make_uint4(0u, 0u, 0u, 0u);
       const int xo_tid = kDThreads - 1 - tid;              // the threads the digit items use least
@@ -522,11 +584,8 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
           const int4 a = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj)), c = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj + 4));
           auto pk = [&](int i0, int i1) { return (uint32_t)ldx16(xr, b, i0) | ((uint32_t)ldx16(xr, b, i1) << 16); };
           xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
-        } else if (xll) {
-          const size_t i0 = ((size_t)b * K + K - r + 8 * jj) >> 1;
-          xo_v = make_uint4(ll_word(xll, i0), ll_word(xll, i0 + 1), ll_word(xll, i0 + 2), ll_word(xll, i0 + 3));
         } else {
-          xo_v = d_ldcg128(xr + K - r + 8 * jj);
+          xo_v = d_ldx128(xr + K - r + 8 * jj, ll_x, pns);
         }
       }
       float rs0 = 1.f, rs1 = 1.f;
@@ -534,21 +593,21 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         // RMSNorm on the way in (HF LlamaRMSNorm / kernel/layernorm/layernorm.cu:25-51): the row's sum of squares needs the
         // whole row: one CTA-wide reduction (only for stages with a norm)
         float ss0 = 0.f, ss1 = 0.f;
-        auto sumsq = [&](const uint4& v0, const uint4& v1, int b) {
-          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        auto sumsq = [&](const uint4& v0, int b) {
+          const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
           float ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+          for (int j = 0; j < 4; ++j) { const float2 f = half2_bits_to_float2(w[j]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
           if (b == 0) ss0 += ss; else ss1 += ss;
         };
-        if (kl0) sumsq(k0a, k0b, kb0);
-        if (kl1) sumsq(k1a, k1b, kb1);
+        if (kl0) sumsq(k0a, kb0);
+        if (kl1) sumsq(k1a, kb1);
         for (int q = 2; q < npass; ++q) {
-          uint4 v0, v1; int b, st; bool live;
-          load_item(q * kDThreads + tid, v0, v1, b, st, live);
-          if (live) sumsq(v0, v1, b);
+          uint4 v0; int b, st; bool live;
+          load_item(q * kDThreads + tid, v0, b, st, live);
+          if (live) sumsq(v0, b);
         }
-        if (xo_tid < nxo) sumsq(xo_v, make_uint4(0u, 0u, 0u, 0u), xo_tid / (r >> 3));
+        if (xo_tid < nxo) sumsq(xo_v, xo_tid / (r >> 3));
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
           ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
@@ -562,75 +621,95 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         rs0 = rsqrtf(ss0 / (float)K + S->norm_eps);
         rs1 = rsqrtf(ss1 / (float)K + S->norm_eps);
       }
-      dec_stamp(L, s, 4);
+      dec_stamp<DBG>(L, s, 4);
       // the reference's two roundings: (x * rs).to(fp16), then * weight in fp16
       auto normed = [&](float v, int col, float rs) { return __half2float(__hmul(nw[col], __float2half_rn(v * rs))); };
       for (int q = 0; q < npass; ++q) {
         const int it = q * kDThreads + tid;
-        uint4 v0, v1; int b, st; bool live;
-        if (q == 0) { v0 = k0a; v1 = k0b; b = kb0; st = ks0; live = kl0; }
-        else if (q == 1) { v0 = k1a; v1 = k1b; b = kb1; st = ks1; live = kl1; }
-        else load_item(it, v0, v1, b, st, live);
+        uint4 v0; int b, st; bool live;
+        if (q == 0) { v0 = k0a; b = kb0; st = ks0; live = kl0; }
+        else if (q == 1) { v0 = k1a; b = kb1; st = ks1; live = kl1; }
+        else load_item(it, v0, b, st, live);
         const bool valid = it < nitems;
-        const int tt = (it >> 1) & 3, hs = it & 1;
-        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        float2 f[8];
+        const int sub = it & 15, tt = sub >> 2, half = (sub >> 1) & 1, hs = sub & 1;
+        const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+        float2 f[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = half2_bits_to_float2(w[j]);
+        for (int j = 0; j < 4; ++j) f[j] = half2_bits_to_float2(w[j]);
         if (nw && live) {
-          const int k0 = st * 128 + tt * 32 + hs * 8;
+          const int k0 = st * 128 + sub * 8;
           const float rs = b ? rs1 : rs0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int k = k0 + (j < 4 ? 2 * j : 16 + 2 * (j - 4));
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 2 * j;
             const int c0 = gat ? gat[k] : k, c1 = gat ? gat[k + 1] : k + 1;
             f[j] = make_float2(normed(f[j].x, c0, rs), normed(f[j].y, c1, rs));
           }
         }
         float sum = 0.f, mx = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           sum += f[j].x + f[j].y;
           mx = fmaxf(mx, fmaxf(fabsf(f[j].x), fabsf(f[j].y)));
         }
 #pragma unroll
-        for (int o = 4; o >= 1; o >>= 1) {
+        for (int o = 8; o >= 1; o >>= 1) {
           sum += __shfl_xor_sync(0xffffffffu, sum, o);
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
+        // 2^e > mx;  X = rint(x 2^(22-e)) by the magic-number add (|X| < 2^22): bits(fma(x, sc, 1.5 2^23)) = 0x4B400000 + X.
+        // A byte of a packed word holds TWO weights: lo (this byte position of the nibble-half hs = 0 item) and hi (the same
+        // position of the hs = 1 item, the lane next door), byte = lo + 16 hi.  The consumers multiply the RAW byte with the
+        // digits of 16 X_lo and the masked byte 16 hi with the digits of X_hi - 16 X_lo:
+        //   sum byte * 16 X_lo + sum 16 hi * (X_hi - 16 X_lo) = 16 (sum lo X_lo + sum hi X_hi),
+        // exactly, in ONE s32 accumulator chain and with one AND mask per word instead of two.  Both operands are below
+        // 2^27 in magnitude: four signed-byte digits V = sum d_i 256^i, the bytes of (V + 0x80808080) ^ 0x80808080.
+        // (all lanes take part: the exchanges with the neighbouring items are shuffles)
+        const int e = mx > 0.f ? (int)((__float_as_uint(mx) >> 23) & 0xff) - 126 : -100;
+        const float sc = e > -100 ? __uint_as_float((uint32_t)(127 + 22 - e) << 23) : 0.f;
+        uint32_t D[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int xa = __float_as_int(fmaf(f[j].x, sc, 12582912.f)) - 0x4B400000;
+          const int xb = __float_as_int(fmaf(f[j].y, sc, 12582912.f)) - 0x4B400000;
+          const int pa = __shfl_xor_sync(0xffffffffu, xa, 1), pb = __shfl_xor_sync(0xffffffffu, xb, 1);
+          const int va = hs ? xa - 16 * pa : 16 * xa, vb = hs ? xb - 16 * pb : 16 * xb;
+          D[2 * j] = ((uint32_t)va + 0x80808080u) ^ 0x80808080u;
+          D[2 * j + 1] = ((uint32_t)vb + 0x80808080u) ^ 0x80808080u;
+        }
+        // Word c (= B-fragment register of lane t = c) of digit column d holds the bytes {first[2c], second[2c], first[2c+1],
+        // second[2c+1]}, first / second = the chunk's columns 0..7 / 16..23 (+ 8 hs): the `half` = 0 item of a pair has the
+        // first[] values, its neighbour two lanes on the second[] ones.  They swap four values each; the half = 0 lane then
+        // writes words c = 0, 1 and the half = 1 lane words c = 2, 3.
+        uint32_t Fv[4], Sv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t send = half ? D[j] : D[4 + j];
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+          Fv[j] = half ? recv : D[j];
+          Sv[j] = half ? D[4 + j] : recv;
+        }
         if (valid) {
-          // 2^e > mx;  X = rint(x 2^(22-e)) by the magic-number add (|X| < 2^22): bits(fma(x, sc, 1.5 2^23)) = 0x4B400000 + X.
-          // Z = X + 0x808080 has unsigned bytes b_i with X = sum (b_i - 128) 256^i: the signed digits are the bytes of Z ^ 0x808080.
-          const int e = mx > 0.f ? (int)((__float_as_uint(mx) >> 23) & 0xff) - 126 : -100;
-          const float sc = e > -100 ? __uint_as_float((uint32_t)(127 + 22 - e) << 23) : 0.f;
-          auto digits = [&](float v) {
-            const int bits = __float_as_int(fmaf(v, sc, 12582912.f));
-            return (uint32_t)(bits + (0x00808080 - 0x4B400000)) ^ 0x00808080u;
-          };
-
-          // Word c of digit column d = bytes {first[2c], second[2c], first[2c+1], second[2c+1]} (first = k0 + ., second =
-          // k0 + 16 + .): the B-fragment register of lane t = c for this item's 32-column chunk tt = 2 T + h and nibble
-          // position hs.  Lane t's 16-byte row of (hs, column) holds its four chunks' words, index tt.
-          const uint32_t dst = xdig + (uint32_t)st * XSTEP + (uint32_t)hs * XHALF + (uint32_t)(4 * b) * 64 + (uint32_t)tt * 4;
+          // lane t's 16-byte row of (hs, column) holds its four chunks' words, index tt
+          const uint32_t dst = xdig + (uint32_t)st * XSTEP + (uint32_t)hs * XHALF + (uint32_t)(4 * b) * 64 + (uint32_t)tt * 4 + (uint32_t)(half * 32);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            // (f[c] = first[2c], first[2c+1]; f[4 + c] = second[2c], second[2c+1]: four digit words live at a time)
-            const uint32_t da = digits(f[c].x), db = digits(f[4 + c].x), dc = digits(f[c].y), dd = digits(f[4 + c].y);
+          for (int cc = 0; cc < 2; ++cc) {
+            const uint32_t da = Fv[2 * cc], db = Sv[2 * cc], dc = Fv[2 * cc + 1], dd = Sv[2 * cc + 1];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
+            for (int d = 0; d < 4; ++d) {
               const uint32_t sel = 0x0040u + 0x11u * (uint32_t)d;
               const uint32_t ww = d_prmt(d_prmt(da, db, sel), d_prmt(dc, dd, sel), 0x5410u);
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + (uint32_t)(d * 64 + c * 16)), "r"(ww) : "memory");
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + (uint32_t)(d * 64 + cc * 16)), "r"(ww) : "memory");
             }
           }
-          if ((it & 7) == 0) {
-            // per step and batch row: {sum of x, weight of digit 0 = 2^(e-22) / 16 (the nibble trick's 16 q)}
+          if (sub == 0) {
+            // per step and batch row: {sum of x, weight of digit 0 = 2^(e-22) / 16 (both operands carry a factor 16)}
             const float cg = e > -100 ? __uint_as_float((uint32_t)(127 + e - 22 - 4) << 23) : 0.f;
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xsum + (uint32_t)(st * 16 + b * 8)), "f"(sum), "f"(cg) : "memory");
           }
         }
       }
-      dec_stamp(L, s, 6);
+      dec_stamp<DBG>(L, s, 6);
       if (xo_tid < nxo) {
         const int b = xo_tid / (r >> 3), jj = xo_tid - b * (r >> 3);
         if (nw) {
@@ -657,13 +736,14 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     if (s + 1 < s_end && tid >= 32 && tid < 32 + (int)(sizeof(DecStage) / 16))
       d_cp16p(d_smem_u32(reinterpret_cast<uint8_t*>(ccache2) + ((s + 1 - s_begin) & 1) * 512) + (uint32_t)(tid - 32) * 16,
               reinterpret_cast<const uint8_t*>(stages + s + 1) + (size_t)(tid - 32) * 16);
-    dec_stamp(L, s, 1);
+    dec_stamp<DBG>(L, s, 1);
     // ---- the tile-blocks of the stage -------------------------------------------------------------------------
+    // The consumers are bound by instruction issue (4 warps per scheduler, every warp the same ~150-instruction chain per
+    // block), so the loop is specialised at compile time: BC = single-k-block stage (K <= 4096 + r) whose B operands stay in
+    // registers for the whole stage; the instrumented paths exist only in the DBG instances.
     {
       const int KB = (ns + kKB - 1) / kKB;
       const uint32_t xo_lane = xo + (uint32_t)((gx * r + 2 * t) * 2);
-      uint4 xe = make_uint4(0u, 0u, 0u, 0u), xq = xe, xe2 = xe, xq2 = xe;
-      float2 xs0 = make_float2(0.f, 0.f), xs1 = xs0;
       // B fragments (digit bytes), group sum and digit weight of one step
       auto load_x = [&](int gs, uint4& xe_, uint4& xq_, float2& xs) {
         const uint32_t xc = xdig_lane + (uint32_t)gs * XSTEP;
@@ -671,122 +751,151 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         d_lds128_if(xq_, xc + XHALF, has_col);
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xs.x), "=f"(xs.y) : "r"(xsum + (uint32_t)(gs * 16 + (M == 2 ? (t >> 1) * 8 : 0))) : "memory");
       };
-      // single-k-block stages (K <= 4096 + r): a warp works on the same two steps of every tile: their B operands are
-      // loaded once per stage and stay in registers
-      const bool bcache = KB == 1;
-      if (bcache) {
-        if (warp < ns) load_x(warp, xe, xq, xs0);
-        if (warp + kDWarps < ns) load_x(warp + kDWarps, xe2, xq2, xs1);
-      }
+      const int nou16 = r >> 4;
+      auto run_tiles = [&](auto bc_tag) {
+        constexpr bool BC = decltype(bc_tag)::value;
+        uint4 xe = make_uint4(0u, 0u, 0u, 0u), xq = xe, xe2 = xe, xq2 = xe;
+        float2 xs0 = make_float2(0.f, 0.f), xs1 = xs0;
+        if (BC) {
+          if (warp < ns) load_x(warp, xe, xq, xs0);
+          if (warp + kDWarps < ns) load_x(warp + kDWarps, xe2, xq2, xs1);
+        }
+        uint32_t sbase = ring + (uint32_t)cslot * (uint32_t)L.slot;
+        uint32_t pdst = part_w;                              // this warp's slice of tile 0
 #pragma unroll 1
-      for (int j = 0; j < R.ntiles; ++j) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};    // rows 2g, 2g+1 x accumulator columns 2t, 2t+1: sum over groups of scale * P
-        float zacc0 = 0.f, zacc1 = 0.f;         // M = 2: rows 2g, 2g+1, sum over groups of scaled zero * X_g, batch row t >> 1
-        float yo[4] = {0.f, 0.f, 0.f, 0.f};     // outlier columns: rows 2g, 2g+1 x batch rows 2t, 2t+1
+        for (int j = 0; j < R.ntiles; ++j) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};    // rows 2g, 2g+1 x accumulator columns 2t, 2t+1: sum over groups of scale * P
+          float zacc0 = 0.f, zacc1 = 0.f;         // M = 2: rows 2g, 2g+1, sum over groups of scaled zero * X_g, batch row t >> 1
+          float yo[4] = {0.f, 0.f, 0.f, 0.f};     // outlier columns: rows 2g, 2g+1 x batch rows 2t, 2t+1
 #pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t sbase = ring + (uint32_t)cslot * (uint32_t)L.slot;
-          // wait for the block (lane 0 polls, so that the loop is warp-uniform); meanwhile help refilling free slots
-          const long long tw0 = dbg ? clock64() : 0;
-          if (dbg && dbg_prev) dbg_fill += tw0 - dbg_prev;   // (block-to-block period inside a stage)
-          dbg_prev = tw0;
-          const bool ready0 = dbg ? d_mbar_test(bars + 8 * cslot, cpar) : true;
-          d_mbar_wait(bars + 8 * cslot, cpar);               // the block's bytes have landed (every lane acquires them)
-          const long long tw1 = dbg ? clock64() : 0;
-          if (dbg) { dbg_wait += tw1 - tw0; ++dbg_nblocks; if (!ready0) ++dbg_nwaited; }
-          const int nsb = ns - kb * kKB < kKB ? ns - kb * kKB : kKB;
-          // one 128-column int4 step of 16 rows: A fragments by ldmatrix from the copied bytes, two AND masks per word
-          // (low nibbles q, high nibbles 16 q: both valid u8), 4 IMMA with exact s32 accumulation; 16 lo + hi = 16 sum(q X).
-          // A warp's two steps of the block (warp, warp + 16) are loaded together and then computed: twice the loads
-          // in flight per warp.
-          auto load_step = [&](int st, uint32_t (&a0)[4], uint32_t (&a1)[4], uint4& xe_, uint4& xq_, uint32_t& sw, uint32_t& zw, float2& xs) {
-            d_ldmatrix_x4(a0, sbase + laneA + (uint32_t)(st * 256));
-            d_ldmatrix_x4(a1, sbase + laneA + (uint32_t)(st * 256 + 128));
-            if (!bcache) load_x(kb * kKB + st, xe_, xq_, xs);
-            sw = d_lds32(sbase + laneS + (uint32_t)(st * 16));
-            zw = M == 2 ? d_lds32(sbase + laneS + (uint32_t)(st * 16 + 8)) : 0u;
-          };
-          auto math_step = [&](const uint32_t (&a0)[4], const uint32_t (&a1)[4], const uint4& xe_, const uint4& xq_, uint32_t sw, uint32_t zw, float2 xs2) {
-            const float xs = xs2.x;
-            constexpr uint32_t kLoM = 0x0f0f0f0fu, kHiM = 0xf0f0f0f0u;
-            int lo[4], hi[4];
-            d_imma0(lo, a0[0] & kLoM, a0[1] & kLoM, a0[2] & kLoM, a0[3] & kLoM, xe_.x, xe_.y);
-            d_imma0(hi, a0[0] & kHiM, a0[1] & kHiM, a0[2] & kHiM, a0[3] & kHiM, xq_.x, xq_.y);
-            d_imma(lo, a1[0] & kLoM, a1[1] & kLoM, a1[2] & kLoM, a1[3] & kLoM, xe_.z, xe_.w);
-            d_imma(hi, a1[0] & kHiM, a1[1] & kHiM, a1[2] & kHiM, a1[3] & kHiM, xq_.z, xq_.w);
-            float2 sc = half2_bits_to_float2(sw);
-            float f0 = (float)(lo[0] * 16 + hi[0]), f2 = (float)(lo[2] * 16 + hi[2]);
-            const float f1 = (float)(lo[1] * 16 + hi[1]), f3 = (float)(lo[3] * 16 + hi[3]);
+          for (int kb = 0; kb < KB; ++kb) {
+            // wait for the block's bytes (every lane acquires them)
+            long long tw0 = 0, tw1 = 0;
+            if constexpr (DBG) {
+              if (dbg) {
+                tw0 = clock64();
+                if (dbg_prev) dbg_fill += tw0 - dbg_prev;      // (block-to-block period inside a stage)
+                dbg_prev = tw0;
+                if (!d_mbar_test(bars + 8 * cslot, cpar)) ++dbg_nwaited;
+              }
+            }
+            d_mbar_wait(bars + 8 * cslot, cpar);
+            if constexpr (DBG) {
+              if (dbg) { tw1 = clock64(); dbg_wait += tw1 - tw0; ++dbg_nblocks; }
+            }
+            const int nsb = BC ? ns : (ns - kb * kKB < kKB ? ns - kb * kKB : kKB);
+            // one 128-column int4 step of 16 rows: A fragments by ldmatrix from the copied bytes; the raw bytes (lo + 16 hi)
+            // against the digits of 16 X_lo, the masked bytes (16 hi) against the digits of X_hi - 16 X_lo (see the staging):
+            // one AND per word, 4 IMMA chained into one exact s32 accumulator = 16 sum(q X) per digit column.
+            // A warp's two steps of the block (warp, warp + 16) are loaded together and then computed: twice the loads
+            // in flight per warp.
+            auto load_step = [&](int st, uint32_t (&a0)[4], uint32_t (&a1)[4], uint4& xe_, uint4& xq_, uint32_t& sw, uint32_t& zw, float2& xs) {
+              d_ldmatrix_x4(a0, sbase + laneA + (uint32_t)(st * 256));
+              d_ldmatrix_x4(a1, sbase + laneA + (uint32_t)(st * 256 + 128));
+              if (!BC) load_x(kb * kKB + st, xe_, xq_, xs);
+              sw = d_lds32(sbase + laneS + (uint32_t)(st * 16));
+              zw = M == 2 ? d_lds32(sbase + laneS + (uint32_t)(st * 16 + 8)) : 0u;
+            };
+            constexpr uint32_t kHiM = 0xf0f0f0f0u;
+            // the step's s32 sums (one per accumulator column) -> fp32, times scale x digit weight, into the tile's sums
+            auto post_step = [&](const int (&ac)[4], uint32_t sw, uint32_t zw, float2 xs2) {
+              const float xs = xs2.x;
+              float2 sc = half2_bits_to_float2(sw);
+              float f0 = (float)ac[0], f2 = (float)ac[2];
+              const float f1 = (float)ac[1], f3 = (float)ac[3];
+              if (M == 1) {
+                if (zlane) { f0 = xs; f2 = xs; }               // scaled zero x group sum of x in the zero-point lane
+                else { sc.x *= xs2.y; sc.y *= xs2.y; }         // digit lanes: scale x the step's digit weight
+              } else {
+                sc.x *= xs2.y; sc.y *= xs2.y;
+                const float2 zz = half2_bits_to_float2(zw);
+                zacc0 = fmaf(zz.x, xs, zacc0);
+                zacc1 = fmaf(zz.y, xs, zacc1);
+              }
+              acc[0] = fmaf(sc.x, f0, acc[0]);
+              acc[1] = fmaf(sc.x, f1, acc[1]);
+              acc[2] = fmaf(sc.y, f2, acc[2]);
+              acc[3] = fmaf(sc.y, f3, acc[3]);
+            };
+            if (warp < nsb && !(dbgsw & 1)) {
+              uint32_t a0[4], a1[4], sw0, zw0;
+              int ac[4];
+              load_step(warp, a0, a1, xe, xq, sw0, zw0, xs0);
+              if (warp + kDWarps < nsb) {
+                // two steps: their IMMA chains are issued alternately (each chain is 4 dependent instructions)
+                uint32_t b0[4], b1[4], sw1, zw1;
+                int bc[4];
+                load_step(warp + kDWarps, b0, b1, xe2, xq2, sw1, zw1, xs1);
+                d_imma0(ac, a0[0], a0[1], a0[2], a0[3], xe.x, xe.y);
+                d_imma0(bc, b0[0], b0[1], b0[2], b0[3], xe2.x, xe2.y);
+                d_imma(ac, a0[0] & kHiM, a0[1] & kHiM, a0[2] & kHiM, a0[3] & kHiM, xq.x, xq.y);
+                d_imma(bc, b0[0] & kHiM, b0[1] & kHiM, b0[2] & kHiM, b0[3] & kHiM, xq2.x, xq2.y);
+                d_imma(ac, a1[0], a1[1], a1[2], a1[3], xe.z, xe.w);
+                d_imma(bc, b1[0], b1[1], b1[2], b1[3], xe2.z, xe2.w);
+                d_imma(ac, a1[0] & kHiM, a1[1] & kHiM, a1[2] & kHiM, a1[3] & kHiM, xq.z, xq.w);
+                d_imma(bc, b1[0] & kHiM, b1[1] & kHiM, b1[2] & kHiM, b1[3] & kHiM, xq2.z, xq2.w);
+                post_step(ac, sw0, zw0, xs0);
+                post_step(bc, sw1, zw1, xs1);
+              } else {
+                d_imma0(ac, a0[0], a0[1], a0[2], a0[3], xe.x, xe.y);
+                d_imma(ac, a0[0] & kHiM, a0[1] & kHiM, a0[2] & kHiM, a0[3] & kHiM, xq.x, xq.y);
+                d_imma(ac, a1[0], a1[1], a1[2], a1[3], xe.z, xe.w);
+                d_imma(ac, a1[0] & kHiM, a1[1] & kHiM, a1[2] & kHiM, a1[3] & kHiM, xq.z, xq.w);
+                post_step(ac, sw0, zw0, xs0);
+              }
+            }
+            if ((BC || kb == KB - 1) && r > 0 && !(dbgsw & 1)) {
+              // 16 fp16 outlier columns of 16 rows per unit: one HMMA; units go to the warps from the top
+#pragma unroll 1
+              for (int u = kDWarps - 1 - warp; u < nou16; u += kDWarps) {
+                const uint4 a4 = d_lds128(sbase + laneO + (uint32_t)(nsb * 16 + u * 128));
+                const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const uint32_t b0 = d_lds32(xo_lane + (uint32_t)(u * 32)), b1 = d_lds32(xo_lane + (uint32_t)(u * 32 + 16));
+                mma_m16n8k16_f16f32(yo, a[0], a[1], a[2], a[3], b0, b1);
+              }
+            }
+            // this warp is done with the slot
+            __syncwarp();
+            if constexpr (DBG) {
+              if (dbg) dbg_math += clock64() - tw1;
+            }
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ebars + 8 * cslot) : "memory");
+            sbase += (uint32_t)L.slot;
+            if (++cslot == NS) { cslot = 0; cpar ^= 1u; sbase = ring; }
+          }
+          {
+            // end of the tile: accumulator columns -> one value per (row, batch row), to this warp's slice of the tile
+            // (digit columns of a batch row weigh 256^i; M = 1: lane t = 2 is the zero-point lane)
+            float v1 = fmaf(dc0, acc[0], dc1 * acc[1]), v2 = fmaf(dc0, acc[2], dc1 * acc[3]);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
             if (M == 1) {
-              if (zlane) { f0 = xs; f2 = xs; }               // scaled zero x group sum of x in the zero-point lane
-              else { sc.x *= xs2.y; sc.y *= xs2.y; }         // digit lanes: scale x the step's digit weight
+              v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+              v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+              if (t == 0) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(pdst), "f"(v1 + yo[0]), "f"(v2 + yo[2]) : "memory");
             } else {
-              sc.x *= xs2.y; sc.y *= xs2.y;
-              const float2 zz = half2_bits_to_float2(zw);
-              zacc0 = fmaf(zz.x, xs, zacc0);
-              zacc1 = fmaf(zz.y, xs, zacc1);
+              // batch row 1's outlier sums live in lane t = 0 of the quad (accumulator column 1)
+              const float o1 = __shfl_sync(0xffffffffu, yo[1], lane & ~3), o3 = __shfl_sync(0xffffffffu, yo[3], lane & ~3);
+              if (t == 0) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(pdst), "f"(v1 + zacc0 + yo[0]), "f"(v2 + zacc1 + yo[2]) : "memory");
+              if (t == 2) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(pdst + 64u), "f"(v1 + zacc0 + o1), "f"(v2 + zacc1 + o3) : "memory");
             }
-            acc[0] = fmaf(sc.x, f0, acc[0]);
-            acc[1] = fmaf(sc.x, f1, acc[1]);
-            acc[2] = fmaf(sc.y, f2, acc[2]);
-            acc[3] = fmaf(sc.y, f3, acc[3]);
-          };
-          if (warp < nsb && !(L.debug & 1)) {
-            uint32_t a0[4], a1[4], b0[4], b1[4], sw0, sw1 = 0, zw0, zw1 = 0;
-            const bool two = warp + kDWarps < nsb;
-            load_step(warp, a0, a1, xe, xq, sw0, zw0, xs0);
-            if (two) load_step(warp + kDWarps, b0, b1, xe2, xq2, sw1, zw1, xs1);
-            math_step(a0, a1, xe, xq, sw0, zw0, xs0);
-            if (two) math_step(b0, b1, xe2, xq2, sw1, zw1, xs1);
-          }
-          if (kb == KB - 1 && r > 0 && !(L.debug & 1)) {
-            // 16 fp16 outlier columns of 16 rows per unit: one HMMA; units go to the warps from the top
-#pragma unroll 1
-            for (int u = kDWarps - 1 - warp; u < (r >> 4); u += kDWarps) {
-              const uint4 a4 = d_lds128(sbase + laneO + (uint32_t)(nsb * 16 + u * 128));
-              const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
-              const uint32_t b0 = d_lds32(xo_lane + (uint32_t)(u * 32)), b1 = d_lds32(xo_lane + (uint32_t)(u * 32 + 16));
-              mma_m16n8k16_f16f32(yo, a[0], a[1], a[2], a[3], b0, b1);
-            }
-          }
-          // this warp is done with the slot
-          __syncwarp();
-          if (dbg) dbg_math += clock64() - tw1;
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ebars + 8 * cslot) : "memory");
-          if (++cslot == NS) { cslot = 0; cpar ^= 1u; }
-        }
-        {
-          // end of the tile: accumulator columns -> one value per (row, batch row), to this warp's slice of the tile
-          // digit columns of a batch row weigh 1, 256, 65536 (the fourth column is unused); M = 1: lane t = 2 is the zero-point lane
-          const float c0 = (M == 1 ? (t == 0 ? 1.f : (t == 1 ? 65536.f : (t == 2 ? 1.f : 0.f))) : ((t & 1) ? 65536.f : 1.f));
-          const float c1 = (M == 1 ? (t == 0 ? 256.f : 0.f) : ((t & 1) ? 0.f : 256.f));
-          float v1 = fmaf(c0, acc[0], c1 * acc[1]), v2 = fmaf(c0, acc[2], c1 * acc[3]);
-          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
-          float* dst = part + (size_t)((j * kDWarps + warp) * M) * 16;
-          if (M == 1) {
-            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-            v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
-            if (t == 0) { dst[2 * g] = v1 + yo[0]; dst[2 * g + 1] = v2 + yo[2]; }
-          } else {
-            // batch row 1's outlier sums live in lane t = 0 of the quad (accumulator column 1)
-            const float o1 = __shfl_sync(0xffffffffu, yo[1], lane & ~3), o3 = __shfl_sync(0xffffffffu, yo[3], lane & ~3);
-            if (t == 0) { dst[2 * g] = v1 + zacc0 + yo[0]; dst[2 * g + 1] = v2 + zacc1 + yo[2]; }
-            if (t == 2) { dst[16 + 2 * g] = v1 + zacc0 + o1; dst[16 + 2 * g + 1] = v2 + zacc1 + o3; }
+            pdst += (uint32_t)(kDWarps * M * 64);
           }
         }
-      }
+      };
+      if (KB == 1) run_tiles(std::true_type{});
+      else run_tiles(std::false_type{});
     }
     dbg_prev = 0;
     asm volatile("cp.async.wait_all;" ::: "memory");        // (the next stage's descriptor)
     d_consumer_sync();
-    dec_stamp(L, s, 2);
+    dec_stamp<DBG>(L, s, 2);
 
     // ---- add the warps' slices in a fixed order, epilogue, store the rows this CTA owns -------------------------
     {
       const int epi = S->epilogue;
       const int nitems = R.ntiles * 16 * M;
-      const uint2* rll = (LL && S->res_ll != nullptr && S->res_src >= s_begin) ? S->res_ll : nullptr;
+      const bool res_poll = LL && S->res_ll != nullptr && S->res_src >= s_begin;   // the residual is produced in this launch
       for (int i0 = warp * 32; i0 < nitems; i0 += kDThreads) {          // whole warps: the pair exchange below is a shuffle
         const int i = i0 + lane;
         const int b = i % M, rr = (i / M) & 15, j = i / (16 * M);
@@ -820,42 +929,24 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             const __half sg = __float2half_rn(gf / (1.f + __expf(-gf)));
             h = __hmul(sg, __float2half_rn(u));
           } else if (S->residual) {
-            __half res;
-            if (rll) {
-              // the residual was produced in this launch: read it from its data-flow words
-              uint2 w;
-              do {
-                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y)
-                             : "l"(rll + (((size_t)b * Pp->N + n) >> 1)) : "memory");
-              } while (w.y != epoch);
-              res = __ushort_as_half((unsigned short)((n & 1) ? (w.x >> 16) : (w.x & 0xffffu)));
-            } else {
-              res = __ushort_as_half(d_ldcg16(S->residual + (size_t)b * Pp->N + n));
-            }
+            const __half res = __ushort_as_half(d_ldx16(S->residual + (size_t)b * Pp->N + n, res_poll, pns));
             h = __hadd(res, h);
           }
-          Pp->y[(size_t)b * Pp->N + n] = h;
-        }
-        // data-flow copy for the stages of this launch that read y: rows n (even) and n + 1 sit M lanes apart
-        const unsigned hb = (unsigned)__half_as_ushort(h);
-        const unsigned hn = LL ? __shfl_down_sync(0xffffffffu, hb, M) : 0u;
-        if (LL && valid && !(n & 1) && uses_ll && Pp->y_ll != nullptr && Pp->ll_consumer < s_end) {
-          uint2 w = make_uint2(hb | (hn << 16), epoch);
-          asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(Pp->y_ll + (((size_t)b * Pp->N + n) >> 1)), "r"(w.x), "r"(w.y) : "memory");
+          if (LL) {
+            // a y that later stages of this launch poll: 0xFFFF means "not yet written", so a NaN result is stored as 0x7E00
+            unsigned short hb = __half_as_ushort(h);
+            if ((hb & 0x7FFFu) > 0x7C00u) hb = 0x7E00u;
+            d_strelaxed16(Pp->y + (size_t)b * Pp->N + n, hb);
+          } else {
+            Pp->y[(size_t)b * Pp->N + n] = h;
+          }
         }
       }
     }
-    if (s + 1 < s_end && !(LL && S->nx_ll && S->nx_src >= s_begin)) {
-      // the next stage waits at a barrier (one signal per CTA: one signal per warp was measured slower -- 16 x 148
-      // atomics on one address per stage)
-      d_consumer_sync();
-      if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
-    }
-    dec_stamp(L, s, 3);
+    dec_stamp<DBG>(L, s, 5);
+    if (s + 1 < s_end && !(LL && S->nx_ll && S->nx_src >= s_begin)) barrier_arrive();   // the next stage waits at a barrier
+    dec_stamp<DBG>(L, s, 3);
   }
-  // the run's epoch becomes the base of the next run's (every CTA read it at its start: this CTA could only get here
-  // after consuming words of all the others)
-  if (LL && uses_ll && cta == 0 && tid == 0) *reinterpret_cast<volatile unsigned*>(sync + 2) = epoch;
   if (dbg && lane == 0) {
     unsigned long long* o = L.stamps + (size_t)(s_end - s_begin) * 32 + (warp == 0 ? 0 : 8);
     o[0] = (unsigned long long)dbg_wait; o[1] = (unsigned long long)dbg_math; o[2] = 0;
@@ -869,6 +960,8 @@ struct DecProgram {
   DecStage* d_stages = nullptr;
   unsigned* d_sync = nullptr;
   unsigned long long* d_stamps = nullptr;
+  DecReset* d_resets = nullptr;
+  int nresets = 0;
   std::vector<void*> side_tables;
   std::vector<DecStage> h_stages;
   int m = 1;
@@ -881,10 +974,12 @@ static int dec_env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int M, bool LL>
+template <int M, bool LL, bool DBG>
 static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, size_t smem, int grid, cudaStream_t stream,
                       int nbar_total, int uses_ll) {
-  auto kern = decode_w4_kernel<M, LL>;
+  auto kern = decode_w4_kernel<M, LL, DBG>;
+  const DecReset* resets = p->d_resets;
+  const int nresets = p->nresets;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -904,7 +999,7 @@ static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, s
   cfg.attrs = attr;
   cfg.numAttrs = (s1 - s0 > 1) ? 1 : 0;        // (barriers or data-flow polling between stages: CTAs wait for one another)
   const DecStage* st = p->d_stages;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L, nbar_total, uses_ll);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L, nbar_total, uses_ll, resets, nresets);
   if (e != cudaSuccess) return (int)e;
   count_launch();
   return QEFT_OK;
@@ -977,14 +1072,25 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
     d.total_q = total_q;
     d.epilogue = q.epilogue;
   }
-  // Data-flow links: a stage whose x (or residual) IS the y of an earlier stage's projection reads it from that
-  // projection's data-flow words (allocated here, owned by the program) instead of waiting at a barrier.
-  const int ll_env = dec_env_int("QEFT_DECODE_LL", 0);      // (read at every creation: tests build both kinds of program)
+  // Data-flow links: a stage whose x (or residual) IS the y of an earlier stage's projection polls that buffer instead of
+  // waiting at a barrier (the kernel's "data-flow by sentinel").  Only a buffer written by exactly ONE projection of the
+  // program can be a flag for itself: anything else (a scratch buffer reused by several stages, a width mismatch) makes
+  // the consuming stage wait at a barrier.  QEFT_DECODE_LL=0 turns data-flow off.
+  const int ll_env = dec_env_int("QEFT_DECODE_LL", 1);      // (read at every creation: tests build both kinds of program)
   for (int s = 0; s < nstages; ++s) {
     DecStage& d = p->h_stages[s];
     d.x_ll = nullptr; d.res_ll = nullptr; d.x_src = -1; d.res_src = -1; d.force_barrier = 0; d.nx_ll = 0; d.nx_src = -1;
   }
-  auto link = [&](const void* ptr, int width, int s, const uint2*& out_ll, int& out_src) -> int {
+  auto writers = [&](const void* ptr) {
+    int n = 0;
+    for (int ps = 0; ps < nstages; ++ps) {
+      const DecStage& pd = p->h_stages[ps];
+      const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
+      for (int i = 0; i < nout; ++i) n += pd.part[i].y == ptr ? 1 : 0;
+    }
+    return n;
+  };
+  auto link = [&](const void* ptr, int width, int s, const void*& out_ll, int& out_src) -> int {
     // the latest earlier stage with a projection whose output buffer is exactly `ptr` ([m, width])
     for (int ps = s - 1; ps >= 0; --ps) {
       DecStage& pd = p->h_stages[ps];
@@ -992,39 +1098,34 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
       for (int i = 0; i < nout; ++i) {
         DecPart& pp = pd.part[i];
         if (pp.y != ptr) continue;
-        if (pp.N != width || (width & 1)) return -1;            // produced in the program, but not linkable: barrier
-        if (!pp.y_ll) {
-          void* buf = nullptr;
-          if (cudaMalloc(&buf, (size_t)m * pp.N * 4) != cudaSuccess) return -2;
-          cudaMemset(buf, 0, (size_t)m * pp.N * 4);
-          p->side_tables.push_back(buf);
-          pp.y_ll = static_cast<uint2*>(buf);
-        }
+        if (pp.N != width || writers(ptr) != 1) return -1;      // produced in the program, but not linkable: barrier
+        pp.y_ll = pp.y;
         if (s < pp.ll_consumer) pp.ll_consumer = s;
-        out_ll = pp.y_ll;
+        out_ll = pp.y;
         out_src = ps;
         return 1;
       }
     }
     return 0;                                                   // not produced by this program: external input
   };
+  std::vector<DecReset> resets;
   if (ll_env) {
     for (int s = 1; s < nstages; ++s) {
       DecStage& d = p->h_stages[s];
       const int rx = link(d.x, d.K, s, d.x_ll, d.x_src);
       int rr = 0;
       if (d.residual) rr = link(d.residual, d.part[0].N, s, d.res_ll, d.res_src);
-      if (rx == -2 || rr == -2) {
-        for (void* b : p->side_tables) cudaFree(b);
-        delete p;
-        return (int)cudaErrorMemoryAllocation;
-      }
       if (rx < 0 || rr < 0) d.force_barrier = 1;
     }
     for (int s = 0; s + 1 < nstages; ++s) {
       const DecStage& nx = p->h_stages[s + 1];
       p->h_stages[s].nx_ll = (nx.x_ll != nullptr && !nx.force_barrier) ? 1 : 0;
       p->h_stages[s].nx_src = nx.x_src;
+    }
+    for (int s = 0; s < nstages; ++s) {
+      const DecStage& d = p->h_stages[s];
+      for (int i = 0; i < d.nparts; ++i)
+        if (d.part[i].y_ll) resets.push_back(DecReset{reinterpret_cast<unsigned short*>(d.part[i].y), m * d.part[i].N, s, d.part[i].ll_consumer, 0});
     }
   }
   // the decode side tables (see dec_build_side_kernel): one per projection, owned by the program
@@ -1059,9 +1160,15 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
   if (e == cudaSuccess) e = cudaMalloc(&p->d_sync, 256);
   if (e == cudaSuccess) e = cudaMemcpy(p->d_stages, p->h_stages.data(), sizeof(DecStage) * (size_t)nstages, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(p->d_sync, 0, 256);
+  p->nresets = (int)resets.size();
+  if (e == cudaSuccess && p->nresets > 0) {
+    e = cudaMalloc(&p->d_resets, sizeof(DecReset) * resets.size());
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_resets, resets.data(), sizeof(DecReset) * resets.size(), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     if (p->d_stages) cudaFree(p->d_stages);
     if (p->d_sync) cudaFree(p->d_sync);
+    if (p->d_resets) cudaFree(p->d_resets);
     for (void* b : p->side_tables) cudaFree(b);
     delete p;
     return (int)e;
@@ -1075,6 +1182,7 @@ extern "C" int qeft_decode_program_destroy(qeft_decode_program_t* prog) {
   DecProgram* p = reinterpret_cast<DecProgram*>(prog);
   cudaFree(p->d_stages);
   cudaFree(p->d_sync);
+  if (p->d_resets) cudaFree(p->d_resets);
   if (p->d_stamps) cudaFree(p->d_stamps);
   for (void* b : p->side_tables) cudaFree(b);
   delete p;
@@ -1086,7 +1194,7 @@ extern "C" __attribute__((visibility("default"))) int qeft_decode_debug_stamps(q
   if (!prog || !host_out) return QEFT_E_NULL;
   DecProgram* p = reinterpret_cast<DecProgram*>(prog);
   if (!p->d_stamps) return QEFT_E_UNSUPPORTED;
-  cudaError_t e = cudaMemcpy(host_out, p->d_stamps, (p->h_stages.size() * 32 + 24) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(host_out, p->d_stamps, (p->h_stages.size() * (32 + 640) + 24) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   return e == cudaSuccess ? QEFT_OK : (int)e;
 }
 
@@ -1142,13 +1250,16 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   L.misc = (int)off; off += misc;
   static const int debug_env = dec_env_int("QEFT_DECODE_DEBUG", 0);
   L.debug = debug_env;
+  static const int poll_env = dec_env_int("QEFT_DECODE_POLL_NS", 0);
+  L.poll_ns = poll_env;
   static const int stamps_env = dec_env_int("QEFT_DECODE_STAMPS", 0);
   if (stamps_env && !p->d_stamps) {
-    const size_t bytes = ((size_t)n * 32 + 24) * sizeof(unsigned long long);
+    const size_t bytes = ((size_t)n * (32 + 640) + 24) * sizeof(unsigned long long);
     if (cudaMalloc(&p->d_stamps, bytes) == cudaSuccess) cudaMemset(p->d_stamps, 0, bytes);
     else p->d_stamps = nullptr;
   }
   L.stamps = p->d_stamps;
+  L.stamps_all = p->d_stamps ? p->d_stamps + (size_t)n * 32 + 24 : nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 // which stages of the range wait at a barrier, and whether any reads data-flow words written in this launch
   int nbar_total = 0, uses_ll = 0;
@@ -1159,9 +1270,14 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
     uses_ll |= ll ? 1 : 0;
     if (d.res_ll != nullptr && d.res_src >= stage_begin) uses_ll = 1;
   }
-  if (uses_ll)
-    return m == 1 ? dec_launch<1, true>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll)
-                  : dec_launch<2, true>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll);
-  return m == 1 ? dec_launch<1, false>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll)
-                : dec_launch<2, false>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll);
+  if (uses_ll) nbar_total += 1;          // the barrier after re-arming the data-flow outputs
+  const bool instrumented = stamps_env != 0 || debug_env != 0;
+#define QEFT_DEC_GO(MM, LLV, DBGV) dec_launch<MM, LLV, DBGV>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll)
+  if (instrumented) {
+    if (uses_ll) return m == 1 ? QEFT_DEC_GO(1, true, true) : QEFT_DEC_GO(2, true, true);
+    return m == 1 ? QEFT_DEC_GO(1, false, true) : QEFT_DEC_GO(2, false, true);
+  }
+  if (uses_ll) return m == 1 ? QEFT_DEC_GO(1, true, false) : QEFT_DEC_GO(2, true, false);
+  return m == 1 ? QEFT_DEC_GO(1, false, false) : QEFT_DEC_GO(2, false, false);
+#undef QEFT_DEC_GO
 }
