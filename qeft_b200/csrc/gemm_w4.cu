@@ -25,6 +25,9 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 namespace qeft {
 
 constexpr int kBK = 64;           // input columns per k-block (one 128-byte swizzle row of fp16)
@@ -80,6 +83,10 @@ struct GemmParams {
   uint32_t* local_count;
   const uint32_t* wait_flag;
   const uint32_t* epoch;
+  // split-K (small M: gridDim.z CTAs share a tile, each over a contiguous range of ring stages): fp32 partial tiles
+  // [split][M][N] and one arrival counter per tile; the CTA that arrives last adds the partials in split order
+  float* ws;
+  unsigned* counters;
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row groups 1024
@@ -108,6 +115,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kXStages + 1];
   __shared__ uint32_t s_tmem_base;
+  __shared__ uint32_t s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t xs0 = (smem_addr(smem_raw) + 1023u) & ~1023u;          // 1024-byte aligned stage ring
   uint8_t* xs_gen = smem_raw + (xs0 - smem_addr(smem_raw));
@@ -121,8 +129,13 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   const int tok0 = blockIdx.x * kBN;
   const int n0 = blockIdx.y * kBM;
   const int nrb = (p.N - n0) >= kBM ? NRB : (p.N - n0) / 128;   // 128-feature blocks of this tile (N % 128 == 0)
-  const int nkb = p.nkb;
-  const int nst = (nkb + Cfg::kKPS - 1) / Cfg::kKPS;     // ring stages
+  // split-K: this CTA's contiguous range of ring stages [st0, st0 + nst) = k-blocks [kb0, nkb)
+  const int nsplit = (int)gridDim.z, split = (int)blockIdx.z;
+  const int nst_all = (p.nkb + Cfg::kKPS - 1) / Cfg::kKPS;
+  const int st0 = (int)(((long long)nst_all * split) / nsplit), st1 = (int)(((long long)nst_all * (split + 1)) / nsplit);
+  const int nst = st1 - st0;                             // ring stages of this CTA
+  const int kb0 = st0 * Cfg::kKPS;
+  const int nkb = min(p.nkb, st1 * Cfg::kKPS);           // (one past) this CTA's last k-block
 
   if (tid == 0) {
     for (int s = 0; s < kXStages; ++s) { mbar_init(x_full(s), 1 + 4 * nrb); mbar_init(x_empty(s), MC ? 2 : 1); }
@@ -160,11 +173,11 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       for (int st = 0; st < nst; ++st) {
         const int s = st % kXStages, use = st / kXStages;
         if (use > 0) mbar_wait(x_empty(s), (uint32_t)((use - 1) & 1));
-        const int nblk = min(kKPS, nkb - st * kKPS);
+        const int nblk = min(kKPS, nkb - (kb0 + st * kKPS));
         if (p.dbg & 2) { mbar_arrive(x_full(s)); continue; }
         mbar_expect_tx(x_full(s), (uint32_t)(nblk * kXTileBytes));
         for (int j = 0; j < nblk; ++j) {
-          const int kb = st * kKPS + j;
+          const int kb = kb0 + st * kKPS + j;
           const int k0 = kb < p.nkb_q ? kb * kBK : p.K - p.r + (kb - p.nkb_q) * kBK;
           const uint32_t dst = xs0 + s * kXStageBytes + j * kXTileBytes;
           if (MC)     // my half of the tokens, to both CTAs (the peer sends the other half)
@@ -181,7 +194,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         const int s = st % kXStages;
         mbar_wait(x_full(s), (uint32_t)((st / kXStages) & 1));
         tc_fence_after();
-        const int nblk = min(kKPS, nkb - st * kKPS);
+        const int nblk = min(kKPS, nkb - (kb0 + st * kKPS));
         for (int j = 0; j < nblk; ++j) {
 #pragma unroll
           for (int k16 = 0; k16 < kBK / 16; ++k16) {
@@ -209,7 +222,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       // write one k-block (64 fp16 of this lane's feature) into its stage; the first block of a stage waits for
       // the stage to be free, the last one publishes the stage
       auto publish = [&](const uint32_t (&v)[32], int kb) {
-        const int st = kb / kKPS, j = kb - st * kKPS;
+        const int st = (kb - kb0) / kKPS, j = (kb - kb0) - st * kKPS;      // (stage relative to this CTA's first)
         const int as = st % kAStages, use = st / kAStages;
         if (j == 0 && use > 0) mbar_wait(a_empty(as), (uint32_t)((use - 1) & 1));
         tc_fence_after();
@@ -222,7 +235,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         }
       };
       // this set's k-blocks: i-th = block (i % KPS) of stage ws + (i / KPS) * sets
-      auto kb_of = [&](int i) { return (ws + (i / kKPS) * kDequantSets) * kKPS + (i % kKPS); };
+      auto kb_of = [&](int i) { return kb0 + (ws + (i / kKPS) * kDequantSets) * kKPS + (i % kKPS); };
       // Register prefetch ring over this set's k-blocks, kPF deep (weights come from L2, ~700 cycles away), scales
       // one group ahead.
       constexpr int kPF = 4;
@@ -319,6 +332,67 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       const float bias = p.bias ? __half2float(p.bias[f]) : 0.f;
       __half* stage = reinterpret_cast<__half*>(xs_gen + (warp - 4) * 2048);   // 32 tokens x 32 features per warp
       const int fw = n0 + 128 * rb + 32 * quad;                                 // first feature of this warp
+      if (nsplit > 1) {
+        // ---- split-K: fp32 partial tile to the workspace; the CTA that arrives last adds all partials of the tile in
+        // split order (deterministic), adds the bias and stores fp16.  (semaphore reduce of gemm_cuda.cu:512-585, here
+        // without the serialisation: only the last arrival reads.)
+        float* wsp = p.ws + (size_t)split * (size_t)p.M * (size_t)p.N;
+        float* stage_f = reinterpret_cast<float*>(xs_gen + (warp - 4) * 4096);   // 32 tokens x 32 features per warp
+#pragma unroll 1
+        for (int tc = ws; tc < kBN / 32; tc += kDequantSets) {
+          if (tok0 + 32 * tc >= p.M) break;
+          uint32_t acc[32];
+          tmem_ld32(lane_taddr + (uint32_t)(kBN * rb + 32 * tc), acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stage_f[i * 32 + lane] = __uint_as_float(acc[i]);
+          __syncwarp();
+          // 32 rows (tokens) of 128 bytes: 8 lanes per row, 4 rows per pass
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int row = pass * 4 + (lane >> 3), piece = lane & 7;
+            const int tok = tok0 + 32 * tc + row;
+            if (tok < p.M)
+              *reinterpret_cast<float4*>(wsp + (size_t)tok * (size_t)p.N + (size_t)(fw + piece * 4)) =
+                  *reinterpret_cast<const float4*>(stage_f + row * 32 + piece * 4);
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        if (tid == 128) s_last = (atomicAdd(p.counters + tile, 1u) == (unsigned)(nsplit - 1)) ? 1u : 0u;
+        asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
+        if (s_last) {
+          __threadfence();
+          const int ntok = min(kBN, p.M - tok0);
+          for (int idx = tid - 128; idx < ntok * 32; idx += kDequantWarps * 32) {
+            const int tok = tok0 + (idx >> 5), c4 = idx & 31;
+            const size_t off = (size_t)tok * (size_t)p.N + (size_t)(n0 + 4 * c4);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < nsplit; ++z) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + (size_t)z * (size_t)p.M * (size_t)p.N + off));
+              a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            if (p.bias) {
+              const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + n0 + 4 * c4);
+              const float2 b01 = half2_bits_to_float2(bb.x), b23 = half2_bits_to_float2(bb.y);
+              a.x += b01.x; a.y += b01.y; a.z += b23.x; a.w += b23.y;
+            }
+            uint2 o;
+            if (BF16) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+              o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            } else {
+              const __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
+              o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            }
+            *reinterpret_cast<uint2*>(p.y + (size_t)tok * (size_t)p.y_ld + (size_t)(n0 + 4 * c4)) = o;
+          }
+          if (tid == 128) p.counters[tile] = 0u;          // ready for the next launch (stream order)
+        }
+      } else
 #pragma unroll 1
       for (int tc = ws; tc < kBN / 32; tc += kDequantSets) {
         uint32_t acc[32];
@@ -413,8 +487,55 @@ int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
   return make_tmap_f16_2d_pitched(map, base, rows, cols, cols, box_rows);
 }
 
+// Split-K workspace: fp32 partial tiles and per-tile arrival counters, one set per (device, stream) so that launches on
+// different streams never share it; grown on demand.  The first split-K launch on a stream allocates (cudaMalloc), so
+// it must happen before that stream is captured into a CUDA graph (a warm-up call, as torch requires anyway).
+struct SplitWs { int dev; cudaStream_t stream; float* ws; size_t bytes; unsigned* counters; };
+constexpr int kSplitCounters = 8192;
+static int split_workspace(cudaStream_t stream, size_t bytes, float** ws, unsigned** counters) {
+  static std::vector<SplitWs> pool;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SplitWs* e = nullptr;
+  for (auto& w : pool)
+    if (w.dev == dev && w.stream == stream) e = &w;
+  if (!e) {
+    pool.push_back(SplitWs{dev, stream, nullptr, 0, nullptr});
+    e = &pool.back();
+    cudaError_t rc = cudaMalloc(&e->counters, kSplitCounters * sizeof(unsigned));
+    if (rc == cudaSuccess) rc = cudaMemset(e->counters, 0, kSplitCounters * sizeof(unsigned));
+    if (rc != cudaSuccess) { pool.pop_back(); return (int)rc; }
+  }
+  if (e->bytes < bytes) {
+    // (work of earlier launches on this stream may still read the old buffer)
+    if (e->ws) { cudaStreamSynchronize(stream); cudaFree(e->ws); e->ws = nullptr; e->bytes = 0; }
+    const size_t want = bytes < ((size_t)16 << 20) ? ((size_t)16 << 20) : bytes;
+    cudaError_t rc = cudaMalloc(&e->ws, want);
+    if (rc != cudaSuccess) return (int)rc;
+    e->bytes = want;
+  }
+  *ws = e->ws;
+  *counters = e->counters;
+  return QEFT_OK;
+}
+
+// number of K splits for a small-M launch: minimise (waves of CTAs) x (ring stages per split), one stage of overhead
+// per split for the partial round trip; every split keeps at least 3 stages
+static int choose_splits(int tiles, int nst, int nsm) {
+  int best = 1;
+  long best_cost = (long)cdiv(tiles, nsm) * nst + 1;
+  for (int sp = 2; sp <= 16 && nst / sp >= 3; ++sp) {
+    const long cost = (long)cdiv(tiles * sp, nsm) * cdiv(nst, sp) + 1 + sp / 2;
+    if (cost < best_cost) { best_cost = cost; best = sp; }
+  }
+  return best;
+}
+
 template <int NRB, int BN, bool MC, bool BF16>
-static int launch_gemm(const void* x, const GemmParams& prm, unsigned flags, cudaStream_t stream) {
+static int launch_gemm(const void* x, const GemmParams& prm_in, unsigned flags, cudaStream_t stream, bool allow_split = false) {
+  GemmParams prm = prm_in;
   using Cfg = GemmCfg<NRB, BN>;
   CUtensorMap xmap;
   int st = make_tmap_f16_2d(&xmap, x, (uint64_t)prm.M, (uint64_t)prm.K, MC ? BN / 2 : BN);
@@ -430,7 +551,20 @@ static int launch_gemm(const void* x, const GemmParams& prm, unsigned flags, cud
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cdiv(prm.M, BN), (unsigned)cdiv(prm.N, Cfg::kBM));
+  int splits = 1;
+  if (allow_split) {
+    static int nsm = 0;
+    if (nsm == 0 && (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)) nsm = 148;
+    static const int split_env = getenv("QEFT_GEMM_SPLITS") ? atoi(getenv("QEFT_GEMM_SPLITS")) : 0;
+    const int tiles = cdiv(prm.M, BN) * cdiv(prm.N, Cfg::kBM), nst = cdiv(prm.nkb, Cfg::kKPS);
+    splits = split_env > 0 ? (split_env < nst ? split_env : nst) : choose_splits(tiles, nst, nsm);
+    if (tiles > kSplitCounters) splits = 1;
+    if (splits > 1) {
+      const int rc = split_workspace(stream, (size_t)splits * (size_t)prm.M * (size_t)prm.N * sizeof(float), &prm.ws, &prm.counters);
+      if (rc != QEFT_OK) return rc;
+    }
+  }
+  cfg.gridDim = dim3((unsigned)cdiv(prm.M, BN), (unsigned)cdiv(prm.N, Cfg::kBM), (unsigned)splits);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -505,9 +639,20 @@ static int gemm_entry(const void* x, const void* qweight, const void* scales, co
   // the plain launch on B200 because L2 bandwidth is not the limiter at these sizes, so it is not the default)
   // bf16: x, oweight and y are bf16 (bias, scales, scaled zeros stay fp16 as in the checkpoint); the int4 columns are
   // dequantised in fp32 with one rounding to bf16
-  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs);
+  // Small M (the reference's split-K tile configurations, gemm_cuda.cu:952-1004): a narrow token tile so that the MMA
+  // and the activation ring do not work on padding, and K split over several CTAs per tile so that all SMs dequantise
+  // (a 4096 x 11008 layer has 32 feature blocks for 148 SMs).  QEFT_GEMM_SMALLM=0 turns it off.
+  static const int smallm_env = getenv("QEFT_GEMM_SMALLM") ? atoi(getenv("QEFT_GEMM_SMALLM")) : 1;
+  if (smallm_env && !gat && M <= 128) {
+    if (dtype == QEFT_DT_BF16)
+      return M <= 64 ? launch_gemm<1, 64, false, true>(x, prm, flags, cs, true) : launch_gemm<1, 128, false, true>(x, prm, flags, cs, true);
+    return M <= 64 ? launch_gemm<1, 64, false, false>(x, prm, flags, cs, true) : launch_gemm<1, 128, false, false>(x, prm, flags, cs, true);
+  }
+  // a few hundred tokens on a narrow layer still leave SMs idle (4096 x 11008 at M = 256: 32 tiles): K is split there too
+  const bool split_ok = smallm_env && !gat && cdiv(M, 256) * (N / 128) <= 74;     // (at most half a wave of tiles)
+  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs, split_ok);
   if (cfg_env == 3 && N % 256 == 0 && !gat) return launch_gemm<1, 256, true, false>(x, prm, flags, cs);
-  return launch_gemm<1, 256, false, false>(x, prm, flags, cs);
+  return launch_gemm<1, 256, false, false>(x, prm, flags, cs, split_ok);
 }
 
 extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,

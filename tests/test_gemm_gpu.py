@@ -46,6 +46,55 @@ def test_gemm_matches_oracle(M, N, K, r, G):
     assert rel_err(got, want) <= REL_TOL, rel_err(got, want)
 
 
+@pytest.mark.parametrize("M,N,K,r,G", [
+    (8, 256, 2048, 128, 128),       # 64-token tile, 2 feature blocks, 17 ring stages: K split over several CTAs per tile
+    (24, 384, 4096, 128, 128),
+    (48, 128, 1024, 64, 128),       # odd number of k-blocks (15 + 1): the last split ends on a half-filled stage
+    (64, 512, 1536, 0, 512),        # per-channel scales, no outlier columns
+    (100, 256, 2048, 128, 256),     # 128-token tile
+    (128, 128, 8192, 128, 128),
+    (300, 256, 4096, 128, 128),     # 256-token tiles, few of them: split as well
+])
+def test_small_m_split_k_matches_oracle(M, N, K, r, G):
+    """8 <= M <= 128 (the reference's split-K tile configurations, gemm_cuda.cu:952-1004): narrow token tile, K split over
+    gridDim.z CTAs per tile, fp32 partials added in split order by the last CTA to arrive.  Deterministic: two launches
+    are bit-equal; the arrival counters are left at zero, so a second launch (and a CUDA-graph replay) works."""
+    L = oracle.synth_layer(N, K, r=r, G=G, seed=M + N + K + r, bias=True)
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    want = oracle.forward(x, L["qweight"], L["scales"], L["scaled_zeros"], L.get("oweight"), L["bias"], group_size=G)
+    got = run_gemm(L, x, bias=L["bias"])
+    assert got.shape == (M, N) and got.dtype == np.float16
+    assert rel_err(got, want) <= REL_TOL, rel_err(got, want)
+    again = run_gemm(L, x, bias=L["bias"])
+    assert np.array_equal(got.view(np.int16), again.view(np.int16))
+
+
+def test_small_m_split_k_under_graph_replay():
+    from qeft_b200 import qeft_cuda
+    M, N, K, r = 16, 512, 4096, 128
+    L = oracle.synth_layer(N, K, r=r, seed=5)
+    x = dev(np.random.default_rng(5).standard_normal((M, K)).astype(np.float16))
+    t = {k: dev(L[k]) for k in ("qweight", "scales", "scaled_zeros", "oweight")}
+    y = torch.empty((M, N), dtype=torch.float16, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):          # warm-up on the capture stream: the split-K workspace is allocated here
+        qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, out=y)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    first = y.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        qeft_cuda.gemm_w4(x, t["qweight"], t["scales"], t["scaled_zeros"], t["oweight"], None, out=y)
+    for _ in range(3):
+        y.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int16), first.view(torch.int16))
+    want = oracle.forward(x.cpu().numpy(), L["qweight"], L["scales"], L["scaled_zeros"], L["oweight"], None)
+    assert rel_err(y.cpu().numpy(), want) <= REL_TOL
+
+
 def test_gemm_reference_signature_uses_all_int4_columns():
     """`gemm_4bit` of the reference has no outlier term: every int4 column counts (gemm_cuda.cu:929-1033)."""
     from qeft_b200 import qeft_cuda
