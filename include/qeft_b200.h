@@ -179,6 +179,20 @@ QEFT_API int qeft_decode_program_create(const qeft_decode_stage_t* stages, int n
 QEFT_API int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_begin, int stage_end, unsigned flags,
                                      qeft_stream_t stream);
 QEFT_API int qeft_decode_program_num_stages(const qeft_decode_program_t* prog);
+/*
+ * Column-sharded programs (batch 1).  Every rank builds the SAME program over its own row slab of every
+ * projection (N = the slab's rows) and then declares which outputs are exchanged:
+ *   qeft_decode_program_set_ranks: barrier_peer[p] = rank p's barrier word (one uint32 per rank, zero-initialised,
+ *     peer-mapped: symmetric memory), used by the two rank barriers of every launch;
+ *   qeft_decode_program_shard(stage, part, y_full_peer): the part's y is this rank's slice [rank * N, (rank + 1) * N) of
+ *     a gathered row [nranks * N] that every rank holds; y_full_peer[p] = the base of rank p's copy (peer-mapped).  The
+ *     kernel stores the slice into every rank's copy straight from its epilogue (NVLink stores), and a later stage whose
+ *     x is the local copy (x == y_full_peer[rank], K == nranks * N) starts on the elements as they arrive: the all-gather
+ *     is the data-flow protocol of the kernel (each fp16 element is its own arrival flag), there is no collective
+ *     call, no fence and no counter per stage.  The copies must not be written by anything else.
+ */
+QEFT_API int qeft_decode_program_set_ranks(qeft_decode_program_t* prog, int nranks, int rank, void* const* barrier_peer);
+QEFT_API int qeft_decode_program_shard(qeft_decode_program_t* prog, int stage, int part, void* const* y_full_peer);
 QEFT_API int qeft_decode_program_destroy(qeft_decode_program_t* prog);
 
 /*

@@ -57,6 +57,8 @@ SIGNATURES = {
     "qeft_decode_program_create": (_i, [C.POINTER(DecodeStage), _i, _i, C.POINTER(C.c_void_p)]),
     "qeft_decode_program_run": (_i, [_vp, _i, _i, _u, _vp]),
     "qeft_decode_program_num_stages": (_i, [_vp]),
+    "qeft_decode_program_set_ranks": (_i, [_vp, _i, _i, C.POINTER(C.c_void_p)]),
+    "qeft_decode_program_shard": (_i, [_vp, _i, _i, C.POINTER(C.c_void_p)]),
     "qeft_decode_program_destroy": (_i, [_vp]),
     "qeft_gemm_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemm_w4_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),

@@ -68,6 +68,12 @@ struct DecPart {
   int side_q;             // bytes per qweight row of `side`
   int N;
   int q_begin;            // first qweight row of this part in the stage-wide numbering (plain stages)
+  // column-sharded programs (qeft_decode_program_shard): y is this rank's slice [N] of a gathered [nranks x N] row that
+  // every rank holds; the rows are stored into EVERY rank's copy (peer-mapped pointers over NVLink, y_peer[p] = this
+  // rank's slice in rank p's buffer); y_full = the local copy's base (what a later stage reads as its x)
+  int nranks;
+  __half* y_peer[QEFT_MAX_RANKS];
+  const void* y_full;
 };
 
 // Builds one part's side table: side[q][s] = {scales[grp(s)][4q..4q+3], szeros[grp(s)][4q..4q+3]} (16 bytes per 128-column
@@ -117,6 +123,9 @@ struct DecStage {
 
 // Data-flow outputs are re-armed at the start of every launch: one entry per projection whose y a later stage polls.
 struct DecReset { unsigned short* y; int n; int prod, cons; int pad; };   // [m x N] halves, producing / first consuming stage
+
+// Column-sharded programs: one counter per rank (peer-mapped), advanced by every rank at the launch's two rank barriers.
+struct DecRanks { int nranks, rank; unsigned* bar_peer[QEFT_MAX_RANKS]; };
 
 struct DecLayout {            // shared-memory carve-up (bytes from the start of dynamic shared memory)
   int nslots, slot;           // ring at offset 0: nslots slots of `slot` bytes: [4 x kQArea packed words][4 x sarea side bytes]
@@ -205,6 +214,11 @@ constexpr unsigned kDfEmpty = 0xFFFFu;
 __device__ __forceinline__ bool d_has_empty(const uint4& v) {
   return (__vcmpeq2(v.x, 0xFFFFFFFFu) | __vcmpeq2(v.y, 0xFFFFFFFFu) | __vcmpeq2(v.z, 0xFFFFFFFFu) | __vcmpeq2(v.w, 0xFFFFFFFFu)) != 0u;
 }
+__device__ __forceinline__ uint4 d_ldrelaxed128_sys(const void* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ uint4 d_ldrelaxed128(const void* p) {
   uint4 r;
 #ifdef QEFT_DEC_POLL_CG
@@ -227,14 +241,27 @@ __device__ __forceinline__ void d_strelaxed16(void* p, unsigned short v) {
 #endif
 }
 // 16 bytes of x: polled until every element has arrived when the producer runs in this launch
+// (ns bit 31: the producers are other GPUs -- system-scope loads; the low bits: back-off between two polls)
 __device__ __forceinline__ uint4 d_ldx128(const void* p, bool poll, unsigned ns) {
   if (!poll) return d_ldcg128(p);
+  if (ns & 0x80000000u) {
+    uint4 v = d_ldrelaxed128_sys(p);
+    while (d_has_empty(v)) v = d_ldrelaxed128_sys(p);
+    return v;
+  }
   uint4 v = d_ldrelaxed128(p);
   while (d_has_empty(v)) { __nanosleep(ns); v = d_ldrelaxed128(p); }
   return v;
 }
 __device__ __forceinline__ unsigned short d_ldx16(const void* p, bool poll, unsigned ns) {
   if (!poll) return d_ldcg16(p);
+  if (ns & 0x80000000u) {
+    unsigned short v;
+    do {
+      asm volatile("ld.relaxed.sys.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+    } while (v == kDfEmpty);
+    return v;
+  }
   unsigned short v = d_ldrelaxed16(p);
   while (v == kDfEmpty) { __nanosleep(ns); v = d_ldrelaxed16(p); }
   return v;
@@ -332,7 +359,7 @@ __device__ __forceinline__ DecTiles dec_tiles(const DecStage* S, int cta, int nc
 template <int M, bool LL, bool DBG>
 __global__ void __maxnreg__(QEFT_DEC_MAXREG)
 decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, unsigned* sync, const DecLayout L,
-                 int nbar_total, int uses_ll, const DecReset* __restrict__ resets, int nresets) {
+                 int nbar_total, int uses_ll, const DecReset* __restrict__ resets, int nresets, const DecRanks RK) {
   extern __shared__ __align__(128) uint8_t dsm[];
   constexpr int NCOLS = 4 * M;
   constexpr uint32_t XSTEP = 128u * NCOLS;                   // digit bytes per 128-column step: [2 nibble halves][NCOLS][4 t][16 B]
@@ -341,7 +368,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const int g = lane >> 2, t = lane & 3;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int NS = L.nslots;
-  const unsigned pns = (unsigned)L.poll_ns;
+  const unsigned pns = RK.nranks > 1 ? 0x80000000u : (unsigned)L.poll_ns;
 
   const uint32_t ring = d_smem_u32(dsm);
   const uint32_t xdig = d_smem_u32(dsm + L.xdig);
@@ -352,9 +379,9 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   float* coef = red + kDWarps * 4;                           // [8] flush weights of a quad's accumulator columns
   const uint32_t bars = d_smem_u32(dsm + L.misc + 512);      // [nslots] "slot filled" mbarriers
   const uint32_t ebars = bars + 64;                          // [nslots] "slot consumed" mbarriers (16 warp arrivals)
-  DecStage* pcache = reinterpret_cast<DecStage*>(dsm + L.misc + 768);     // descriptor of the producer's stage
-  DecStage* ccache2 = reinterpret_cast<DecStage*>(dsm + L.misc + 1536);   // descriptors of the stage being consumed / the next one
-  static_assert(sizeof(DecStage) <= 512 && sizeof(DecStage) % 4 == 0, "descriptor cache slots are 512 bytes");
+  DecStage* pcache = reinterpret_cast<DecStage*>(dsm + L.misc + 1024);    // descriptor of the producer's stage
+  DecStage* ccache2 = reinterpret_cast<DecStage*>(dsm + L.misc + 2048);   // descriptors of the stage being consumed / the next one
+  static_assert(sizeof(DecStage) <= 1024 && sizeof(DecStage) % 4 == 0, "descriptor cache slots are 1024 bytes");
   constexpr int kStageWords = (int)(sizeof(DecStage) / 4);
 
   if (tid == 0) {
@@ -484,6 +511,33 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     }
     d_consumer_sync();
   };
+  // Column-sharded programs: barrier over all ranks.  Every CTA orders its earlier stores (local resets, peer stores) with
+  // a system-scope fence and arrives at the local grid barrier; CTA 0 then adds one to every rank's counter and waits until
+  // its own has been advanced by every rank; a second grid barrier holds the other CTAs until then.
+  unsigned rk_done = 0;                                      // rank barriers this program has passed before this launch
+  int rk_now = 0;
+  if (RK.nranks > 1 && cta == 0 && tid == 0) rk_done = *reinterpret_cast<volatile unsigned*>(sync + 3);
+  auto rank_barrier = [&]() {
+    d_consumer_sync();
+    if (tid == 0) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
+    }
+    barrier_wait();
+    if (cta == 0 && tid == 0) {
+      ++rk_now;
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      for (int pr = 0; pr < RK.nranks; ++pr)
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(RK.bar_peer[pr]), "r"(1u) : "memory");
+      const unsigned want = (rk_done + (unsigned)rk_now) * (unsigned)RK.nranks;
+      unsigned got;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(RK.bar_peer[RK.rank]) : "memory");
+      } while ((int)(got - want) < 0);
+    }
+    barrier_arrive();
+    barrier_wait();
+  };
   if (LL && uses_ll) {
     // re-arm the data-flow outputs of this launch (one list entry per thread, this CTA's share of its elements), then
     // one grid barrier: nobody polls a buffer that still holds the previous run's results
@@ -494,13 +548,17 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         for (int k = i0; k < i1; ++k) d_strelaxed16(e.y + k, (unsigned short)kDfEmpty);
       }
     }
-    barrier_arrive();
-    barrier_wait();
+    if (RK.nranks > 1) {
+      rank_barrier();         // no rank stores into a peer's buffer before that peer has re-armed it
+    } else {
+      barrier_arrive();
+      barrier_wait();
+    }
   }
 
 #pragma unroll 1
   for (int s = s_begin; s < s_end; ++s) {
-    const DecStage* S = reinterpret_cast<const DecStage*>(reinterpret_cast<const uint8_t*>(ccache2) + ((s - s_begin) & 1) * 512);
+    const DecStage* S = reinterpret_cast<const DecStage*>(reinterpret_cast<const uint8_t*>(ccache2) + ((s - s_begin) & 1) * 1024);
 
     // x produced by an earlier stage of this launch and readable by data-flow: the stage polls the elements it reads,
     // no barrier.  Every other stage after the first waits until all CTAs have stored their rows of the previous one.
@@ -734,7 +792,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     // and the copy lands long before the post-consume barrier after which the next stage reads it
     static_assert(sizeof(DecStage) % 16 == 0, "the descriptor is copied in 16-byte pieces");
     if (s + 1 < s_end && tid >= 32 && tid < 32 + (int)(sizeof(DecStage) / 16))
-      d_cp16p(d_smem_u32(reinterpret_cast<uint8_t*>(ccache2) + ((s + 1 - s_begin) & 1) * 512) + (uint32_t)(tid - 32) * 16,
+      d_cp16p(d_smem_u32(reinterpret_cast<uint8_t*>(ccache2) + ((s + 1 - s_begin) & 1) * 1024) + (uint32_t)(tid - 32) * 16,
               reinterpret_cast<const uint8_t*>(stages + s + 1) + (size_t)(tid - 32) * 16);
     dec_stamp<DBG>(L, s, 1);
     // ---- the tile-blocks of the stage -------------------------------------------------------------------------
@@ -936,7 +994,13 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             // a y that later stages of this launch poll: 0xFFFF means "not yet written", so a NaN result is stored as 0x7E00
             unsigned short hb = __half_as_ushort(h);
             if ((hb & 0x7FFFu) > 0x7C00u) hb = 0x7E00u;
-            d_strelaxed16(Pp->y + (size_t)b * Pp->N + n, hb);
+            if (Pp->nranks > 1) {
+              // column-sharded: this rank's slice of the gathered row, into every rank's copy (NVLink stores; batch 1)
+              for (int pr = 0; pr < Pp->nranks; ++pr)
+                asm volatile("st.relaxed.sys.global.u16 [%0], %1;" ::"l"(Pp->y_peer[pr] + n), "h"(hb) : "memory");
+            } else {
+              d_strelaxed16(Pp->y + (size_t)b * Pp->N + n, hb);
+            }
           } else {
             Pp->y[(size_t)b * Pp->N + n] = h;
           }
@@ -946,6 +1010,11 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     dec_stamp<DBG>(L, s, 5);
     if (s + 1 < s_end && !(LL && S->nx_ll && S->nx_src >= s_begin)) barrier_arrive();   // the next stage waits at a barrier
     dec_stamp<DBG>(L, s, 3);
+  }
+  if (LL && RK.nranks > 1) {
+    // every rank's slices of the last outputs have landed everywhere when the launch ends
+    rank_barrier();
+    if (cta == 0 && tid == 0) *reinterpret_cast<volatile unsigned*>(sync + 3) = rk_done + (unsigned)rk_now;
   }
   if (dbg && lane == 0) {
     unsigned long long* o = L.stamps + (size_t)(s_end - s_begin) * 32 + (warp == 0 ? 0 : 8);
@@ -962,6 +1031,9 @@ struct DecProgram {
   unsigned long long* d_stamps = nullptr;
   DecReset* d_resets = nullptr;
   int nresets = 0;
+  int ll_env = 1;
+  bool dirty = false;           // the description changed since the last upload (qeft_decode_program_shard)
+  DecRanks ranks = {};          // column-sharded programs: the ranks' barrier counters
   std::vector<void*> side_tables;
   std::vector<DecStage> h_stages;
   int m = 1;
@@ -980,6 +1052,7 @@ static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, s
   auto kern = decode_w4_kernel<M, LL, DBG>;
   const DecReset* resets = p->d_resets;
   const int nresets = p->nresets;
+  const DecRanks ranks = p->ranks;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -997,12 +1070,87 @@ static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, s
   attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: they wait for one another at stage boundaries
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (s1 - s0 > 1) ? 1 : 0;        // (barriers or data-flow polling between stages: CTAs wait for one another)
+  cfg.numAttrs = (s1 - s0 > 1 || p->ranks.nranks > 1) ? 1 : 0;        // (barriers or data-flow polling between stages: CTAs wait for one another)
   const DecStage* st = p->d_stages;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L, nbar_total, uses_ll, resets, nresets);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, s0, s1, p->d_sync, L, nbar_total, uses_ll, resets, nresets, ranks);
   if (e != cudaSuccess) return (int)e;
   count_launch();
   return QEFT_OK;
+}
+
+// Data-flow links: a stage whose x (or residual) IS the y of an earlier stage's projection polls that buffer instead of
+// waiting at a barrier (the kernel's "data-flow by sentinel").  Only a buffer written by exactly ONE projection of the
+// program can be a flag for itself: anything else (a scratch buffer reused by several stages, a width mismatch) makes
+// the consuming stage wait at a barrier.  QEFT_DECODE_LL=0 turns data-flow off.  For a column-sharded projection
+// (qeft_decode_program_shard) "the y" is the local copy of the gathered row.  Recomputed and uploaded whenever the
+// program's description changes.
+static int dec_link(DecProgram* p) {
+  const int nstages = (int)p->h_stages.size(), m = p->m;
+  auto out_of = [](const DecPart& pp) -> const void* { return pp.nranks > 1 ? pp.y_full : static_cast<const void*>(pp.y); };
+  auto width_of = [](const DecPart& pp) { return pp.nranks > 1 ? pp.nranks * pp.N : pp.N; };
+  for (int s = 0; s < nstages; ++s) {
+    DecStage& d = p->h_stages[s];
+    d.x_ll = nullptr; d.res_ll = nullptr; d.x_src = -1; d.res_src = -1; d.force_barrier = 0; d.nx_ll = 0; d.nx_src = -1;
+    for (int i = 0; i < d.nparts; ++i) { d.part[i].y_ll = nullptr; d.part[i].ll_consumer = 1 << 30; }
+  }
+  auto writers = [&](const void* ptr) {
+    int n = 0;
+    for (int ps = 0; ps < nstages; ++ps) {
+      const DecStage& pd = p->h_stages[ps];
+      const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
+      for (int i = 0; i < nout; ++i) n += out_of(pd.part[i]) == ptr ? 1 : 0;
+    }
+    return n;
+  };
+  auto link = [&](const void* ptr, int width, int s, const void*& out_ll, int& out_src) -> int {
+    // the latest earlier stage with a projection whose output buffer is exactly `ptr` ([m, width])
+    for (int ps = s - 1; ps >= 0; --ps) {
+      DecStage& pd = p->h_stages[ps];
+      const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
+      for (int i = 0; i < nout; ++i) {
+        DecPart& pp = pd.part[i];
+        if (out_of(pp) != ptr) continue;
+        if (width_of(pp) != width || writers(ptr) != 1) return -1;   // produced in the program, but not linkable: barrier
+        pp.y_ll = ptr;
+        if (s < pp.ll_consumer) pp.ll_consumer = s;
+        out_ll = ptr;
+        out_src = ps;
+        return 1;
+      }
+    }
+    return 0;                                                   // not produced by this program: external input
+  };
+  std::vector<DecReset> resets;
+  if (p->ll_env) {
+    for (int s = 1; s < nstages; ++s) {
+      DecStage& d = p->h_stages[s];
+      const int rx = link(d.x, d.K, s, d.x_ll, d.x_src);
+      int rr = 0;
+      if (d.residual) rr = link(d.residual, d.part[0].N, s, d.res_ll, d.res_src);
+      if (rx < 0 || rr < 0) d.force_barrier = 1;
+    }
+    for (int s = 0; s + 1 < nstages; ++s) {
+      const DecStage& nx = p->h_stages[s + 1];
+      p->h_stages[s].nx_ll = (nx.x_ll != nullptr && !nx.force_barrier) ? 1 : 0;
+      p->h_stages[s].nx_src = nx.x_src;
+    }
+    for (int s = 0; s < nstages; ++s) {
+      const DecStage& d = p->h_stages[s];
+      for (int i = 0; i < d.nparts; ++i)
+        if (d.part[i].y_ll)
+          resets.push_back(DecReset{reinterpret_cast<unsigned short*>(const_cast<void*>(d.part[i].y_ll)), m * width_of(d.part[i]), s,
+                                    d.part[i].ll_consumer, 0});
+    }
+  }
+  cudaError_t e = cudaMemcpy(p->d_stages, p->h_stages.data(), sizeof(DecStage) * (size_t)nstages, cudaMemcpyHostToDevice);
+  if (p->d_resets) { cudaFree(p->d_resets); p->d_resets = nullptr; }
+  p->nresets = (int)resets.size();
+  if (e == cudaSuccess && p->nresets > 0) {
+    e = cudaMalloc(&p->d_resets, sizeof(DecReset) * resets.size());
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_resets, resets.data(), sizeof(DecReset) * resets.size(), cudaMemcpyHostToDevice);
+  }
+  p->dirty = false;
+  return (int)e;
 }
 
 }  // namespace qeft
@@ -1072,62 +1220,6 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
     d.total_q = total_q;
     d.epilogue = q.epilogue;
   }
-  // Data-flow links: a stage whose x (or residual) IS the y of an earlier stage's projection polls that buffer instead of
-  // waiting at a barrier (the kernel's "data-flow by sentinel").  Only a buffer written by exactly ONE projection of the
-  // program can be a flag for itself: anything else (a scratch buffer reused by several stages, a width mismatch) makes
-  // the consuming stage wait at a barrier.  QEFT_DECODE_LL=0 turns data-flow off.
-  const int ll_env = dec_env_int("QEFT_DECODE_LL", 1);      // (read at every creation: tests build both kinds of program)
-  for (int s = 0; s < nstages; ++s) {
-    DecStage& d = p->h_stages[s];
-    d.x_ll = nullptr; d.res_ll = nullptr; d.x_src = -1; d.res_src = -1; d.force_barrier = 0; d.nx_ll = 0; d.nx_src = -1;
-  }
-  auto writers = [&](const void* ptr) {
-    int n = 0;
-    for (int ps = 0; ps < nstages; ++ps) {
-      const DecStage& pd = p->h_stages[ps];
-      const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
-      for (int i = 0; i < nout; ++i) n += pd.part[i].y == ptr ? 1 : 0;
-    }
-    return n;
-  };
-  auto link = [&](const void* ptr, int width, int s, const void*& out_ll, int& out_src) -> int {
-    // the latest earlier stage with a projection whose output buffer is exactly `ptr` ([m, width])
-    for (int ps = s - 1; ps >= 0; --ps) {
-      DecStage& pd = p->h_stages[ps];
-      const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
-      for (int i = 0; i < nout; ++i) {
-        DecPart& pp = pd.part[i];
-        if (pp.y != ptr) continue;
-        if (pp.N != width || writers(ptr) != 1) return -1;      // produced in the program, but not linkable: barrier
-        pp.y_ll = pp.y;
-        if (s < pp.ll_consumer) pp.ll_consumer = s;
-        out_ll = pp.y;
-        out_src = ps;
-        return 1;
-      }
-    }
-    return 0;                                                   // not produced by this program: external input
-  };
-  std::vector<DecReset> resets;
-  if (ll_env) {
-    for (int s = 1; s < nstages; ++s) {
-      DecStage& d = p->h_stages[s];
-      const int rx = link(d.x, d.K, s, d.x_ll, d.x_src);
-      int rr = 0;
-      if (d.residual) rr = link(d.residual, d.part[0].N, s, d.res_ll, d.res_src);
-      if (rx < 0 || rr < 0) d.force_barrier = 1;
-    }
-    for (int s = 0; s + 1 < nstages; ++s) {
-      const DecStage& nx = p->h_stages[s + 1];
-      p->h_stages[s].nx_ll = (nx.x_ll != nullptr && !nx.force_barrier) ? 1 : 0;
-      p->h_stages[s].nx_src = nx.x_src;
-    }
-    for (int s = 0; s < nstages; ++s) {
-      const DecStage& d = p->h_stages[s];
-      for (int i = 0; i < d.nparts; ++i)
-        if (d.part[i].y_ll) resets.push_back(DecReset{reinterpret_cast<unsigned short*>(d.part[i].y), m * d.part[i].N, s, d.part[i].ll_consumer, 0});
-    }
-  }
   // the decode side tables (see dec_build_side_kernel): one per projection, owned by the program
   for (int s = 0; s < nstages; ++s) {
     DecStage& d = p->h_stages[s];
@@ -1158,13 +1250,9 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
   if (cudaDeviceGetAttribute(&p->nsm, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess || p->nsm <= 0) p->nsm = 148;
   cudaError_t e = cudaMalloc(&p->d_stages, sizeof(DecStage) * (size_t)nstages);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_sync, 256);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_stages, p->h_stages.data(), sizeof(DecStage) * (size_t)nstages, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(p->d_sync, 0, 256);
-  p->nresets = (int)resets.size();
-  if (e == cudaSuccess && p->nresets > 0) {
-    e = cudaMalloc(&p->d_resets, sizeof(DecReset) * resets.size());
-    if (e == cudaSuccess) e = cudaMemcpy(p->d_resets, resets.data(), sizeof(DecReset) * resets.size(), cudaMemcpyHostToDevice);
-  }
+  p->ll_env = dec_env_int("QEFT_DECODE_LL", 1);             // (read at every creation: tests build both kinds of program)
+  if (e == cudaSuccess) e = (cudaError_t)dec_link(p);
   if (e != cudaSuccess) {
     if (p->d_stages) cudaFree(p->d_stages);
     if (p->d_sync) cudaFree(p->d_sync);
@@ -1198,6 +1286,42 @@ extern "C" __attribute__((visibility("default"))) int qeft_decode_debug_stamps(q
   return e == cudaSuccess ? QEFT_OK : (int)e;
 }
 
+extern "C" int qeft_decode_program_set_ranks(qeft_decode_program_t* prog, int nranks, int rank, void* const* barrier_peer) {
+  if (!prog || !barrier_peer) return QEFT_E_NULL;
+  if (nranks < 1 || nranks > QEFT_MAX_RANKS || rank < 0 || rank >= nranks) return QEFT_E_SHAPE;
+  DecProgram* p = reinterpret_cast<DecProgram*>(prog);
+  if (p->m != 1) return QEFT_E_BATCH;
+  p->ranks.nranks = nranks;
+  p->ranks.rank = rank;
+  for (int i = 0; i < nranks; ++i) {
+    if (!barrier_peer[i]) return QEFT_E_NULL;
+    p->ranks.bar_peer[i] = static_cast<unsigned*>(barrier_peer[i]);
+  }
+  return QEFT_OK;
+}
+
+extern "C" int qeft_decode_program_shard(qeft_decode_program_t* prog, int stage, int part, void* const* y_full_peer) {
+  if (!prog || !y_full_peer) return QEFT_E_NULL;
+  DecProgram* p = reinterpret_cast<DecProgram*>(prog);
+  const int P = p->ranks.nranks, rank = p->ranks.rank;
+  if (P < 2) return QEFT_E_UNSUPPORTED;                      // qeft_decode_program_set_ranks first
+  if (stage < 0 || stage >= (int)p->h_stages.size()) return QEFT_E_SHAPE;
+  DecStage& d = p->h_stages[stage];
+  const int nout = d.epilogue == QEFT_EPI_SWIGLU ? 1 : d.nparts;
+  if (part < 0 || part >= nout) return QEFT_E_SHAPE;
+  DecPart& dp = d.part[part];
+  for (int i = 0; i < P; ++i) {
+    if (!y_full_peer[i]) return QEFT_E_NULL;
+    if (!check_align16(y_full_peer[i])) return QEFT_E_ALIGN;
+    dp.y_peer[i] = static_cast<__half*>(y_full_peer[i]) + (size_t)rank * dp.N;
+  }
+  dp.nranks = P;
+  dp.y_full = y_full_peer[rank];
+  dp.y = dp.y_peer[rank];
+  p->dirty = true;
+  return QEFT_OK;
+}
+
 extern "C" int qeft_decode_program_num_stages(const qeft_decode_program_t* prog) {
   return prog ? (int)reinterpret_cast<const DecProgram*>(prog)->h_stages.size() : QEFT_E_NULL;
 }
@@ -1209,6 +1333,10 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   DecProgram* p = reinterpret_cast<DecProgram*>(prog);
   const int n = (int)p->h_stages.size();
   if (stage_begin < 0 || stage_end > n || stage_begin >= stage_end) return QEFT_E_SHAPE;
+  if (p->dirty) {                                            // (re-links and uploads: not inside a stream capture)
+    const int rc = dec_link(p);
+    if (rc != QEFT_OK) return rc;
+  }
   static const int grid_env = dec_env_int("QEFT_DECODE_GRID", 0);
   static const int slots_env = dec_env_int("QEFT_DECODE_SLOTS", 0);
   const int grid = grid_env > 0 ? grid_env : p->nsm;
@@ -1232,7 +1360,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
   const size_t xsum = (size_t)max_steps * 16 + 16;
   const size_t xo = (size_t)m * max_r * 2 + 16;
   const size_t part = (size_t)max_tiles * kDWarps * m * 16 * sizeof(float);
-  const size_t misc = 3072;
+  const size_t misc = 4096;
   const size_t fixed = ((xdig + 127) & ~(size_t)127) + ((xsum + 127) & ~(size_t)127) + ((xo + 127) & ~(size_t)127) +
                        ((part + 127) & ~(size_t)127) + misc;
   if (fixed + 2 * (size_t)L.slot > kDSmemMax) return QEFT_E_UNSUPPORTED;
@@ -1270,14 +1398,17 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
     uses_ll |= ll ? 1 : 0;
     if (d.res_ll != nullptr && d.res_src >= stage_begin) uses_ll = 1;
   }
-  if (uses_ll) nbar_total += 1;          // the barrier after re-arming the data-flow outputs
+  const bool sharded = p->ranks.nranks > 1;
+  if (sharded && !p->ll_env) return QEFT_E_UNSUPPORTED;      // the exchange between ranks IS the data-flow protocol
+  if (uses_ll) nbar_total += sharded ? 2 : 1;                // the barrier after re-arming the data-flow outputs
+  if (sharded) nbar_total += 2;                              // the rank barrier that ends the launch
   const bool instrumented = stamps_env != 0 || debug_env != 0;
 #define QEFT_DEC_GO(MM, LLV, DBGV) dec_launch<MM, LLV, DBGV>(p, stage_begin, stage_end, L, off, grid, st, nbar_total, uses_ll)
   if (instrumented) {
-    if (uses_ll) return m == 1 ? QEFT_DEC_GO(1, true, true) : QEFT_DEC_GO(2, true, true);
+    if (uses_ll || sharded) return m == 1 ? QEFT_DEC_GO(1, true, true) : QEFT_DEC_GO(2, true, true);
     return m == 1 ? QEFT_DEC_GO(1, false, true) : QEFT_DEC_GO(2, false, true);
   }
-  if (uses_ll) return m == 1 ? QEFT_DEC_GO(1, true, false) : QEFT_DEC_GO(2, true, false);
+  if (uses_ll || sharded) return m == 1 ? QEFT_DEC_GO(1, true, false) : QEFT_DEC_GO(2, true, false);
   return m == 1 ? QEFT_DEC_GO(1, false, false) : QEFT_DEC_GO(2, false, false);
 #undef QEFT_DEC_GO
 }

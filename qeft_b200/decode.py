@@ -100,7 +100,7 @@ class PackedDecoderStack:
         self.program = qeft_cuda.DecodeProgram(stages, m=self.batch)
         return self.program
 
-    def enable_chain_program(self, dataflow=False, eps=1e-5):
+    def enable_chain_program(self, dataflow=False, eps=1e-5, ln=None, hidden=None):
         """The token as ONE launch in which the stages really feed each other, with a Llama block's elementwise glue
         fused in: per block [RMSNorm -> q|k|v], [o_proj (reorder gather) + residual], [RMSNorm -> gate|up ->
         SiLU*mul], [down_proj + residual]; the next block's q|k|v reads this block's output.  Attention is not part of
@@ -113,10 +113,10 @@ class PackedDecoderStack:
         m, dev = self.batch, self.device
         g = torch.Generator(device=dev)
         g.manual_seed(4242)
-        self.ln = [(1 + 0.1 * torch.randn((2, self.h), device=dev, generator=g)).half() for _ in self.blocks]
+        self.ln = ln if ln is not None else [(1 + 0.1 * torch.randn((2, self.h), device=dev, generator=g)).half() for _ in self.blocks]
         self.chain = []
         stages = []
-        hidden = self.x_h
+        hidden = self.x_h if hidden is None else hidden
 
         def parts(blk, names, ys):
             return [{"qweight": blk[n]["qweight"], "scales": blk[n]["scales"], "scaled_zeros": blk[n]["scaled_zeros"],
@@ -151,6 +151,115 @@ class PackedDecoderStack:
                 os.environ["QEFT_DECODE_LL"] = old
         self.chain_mode = "dataflow" if dataflow else "barrier"
         return self.program
+
+    def enable_sharded_chain_program(self, process_group, eps=1e-5):
+        """The chained token of :meth:`enable_chain_program` on a column-sharded stack, as ONE launch per rank with the
+        all-gathers inside the kernel: every projection computes this rank's row slab and stores its slice of the
+        gathered activation row straight into every rank's copy (symmetric memory, NVLink stores); the next stage starts
+        on the elements as they arrive (data-flow by sentinel: no collective call, no fence, no counter per stage; two
+        rank barriers per token).  SURVEY.md 8e; replaces the per-launch exchange of :meth:`enable_fused_gather`."""
+        import torch.distributed._symmetric_memory as symm_mem
+        assert self.batch == 1 and self.fused and self.kv % self.world == 0
+        P, rank, dev = self.world, self.rank, self.device
+        g = torch.Generator(device=dev)
+        g.manual_seed(4242)
+        self.ln = [(1 + 0.1 * torch.randn((2, self.h), device=dev, generator=g)).half() for _ in self.blocks]
+        # one symmetric allocation: [barrier word | per block: q, k, v, h2, act, out gathered rows]
+        widths = {"q": self.h, "k": self.kv, "v": self.kv, "h2": self.h, "act": self.f, "out": self.h}
+        per_block = sum(widths.values()) * 2
+        total = 256 + per_block * len(self.blocks)
+        buf = symm_mem.empty((total,), dtype=torch.uint8, device=dev)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, process_group)
+        self._symm = (buf, hdl)
+        self.chain, stages, offs = [], [], []
+        hidden = self.x_h
+        off = 256
+
+        def parts(blk, names, ys):
+            return [{"qweight": blk[n]["qweight"], "scales": blk[n]["scales"], "scaled_zeros": blk[n]["scaled_zeros"],
+                     "oweight": blk[n].get("oweight"), "bias": blk[n].get("bias"), "N": blk[n]["N"], "y": y}
+                    for n, y in zip(names, ys)]
+
+        for li, blk in enumerate(self.blocks):
+            full, o = {}, {}
+            for name, w in widths.items():
+                full[name] = buf[off:off + 2 * w].view(torch.float16).view(1, w)
+                o[name] = off
+                off += 2 * w
+            up = torch.empty((1, self.nf), dtype=torch.float16, device=dev)
+
+            def mine(name, n_local):       # this rank's slice of the local copy
+                return full[name][:, rank * n_local:(rank + 1) * n_local]
+
+            kw = {"K": self.h, "r": self.r, "G": self.G}
+            stages.append({"x": hidden, **kw, "norm_weight": self.ln[li][0], "norm_eps": eps,
+                           "parts": parts(blk, ("q", "k", "v"), (mine("q", self.nq), mine("k", self.nkv), mine("v", self.nkv)))})
+            st = {"x": full["q"], **kw, "epilogue": "residual", "residual": hidden[:, rank * self.no:(rank + 1) * self.no],
+                  "parts": parts(blk, ("o",), (mine("h2", self.no),))}
+            if self.r > 0:
+                st["x_gather"] = blk["o"]["reorder_ids32"]
+            stages.append(st)
+            stages.append({"x": full["h2"], **kw, "norm_weight": self.ln[li][1], "norm_eps": eps, "epilogue": "swiglu",
+                           "parts": parts(blk, ("gate", "up"), (mine("act", self.nf), up))})
+            stages.append({"x": full["act"], "K": self.f, "r": self.r, "G": self.G, "epilogue": "residual",
+                           "residual": full["h2"][:, rank * self.no:(rank + 1) * self.no],
+                           "parts": parts(blk, ("down",), (mine("out", self.no),))})
+            self.chain.append(full)
+            offs.append(o)
+            hidden = full["out"]
+        prog = qeft_cuda.DecodeProgram(stages, m=1)
+        prog.set_ranks(P, rank, [hdl.buffer_ptrs[p] for p in range(P)])
+        for li, o in enumerate(offs):
+            for si, names in enumerate((("q", "k", "v"), ("h2",), ("act",), ("out",))):
+                for pi, name in enumerate(names):
+                    prog.shard(4 * li + si, pi, [hdl.buffer_ptrs[p] + o[name] for p in range(P)])
+        hdl.barrier()
+        self.program = prog
+        self.chain_mode = "sharded_dataflow"
+        self.fused_gather = None
+        self.pg = None
+        return prog
+
+    def gathered_twin(self, layers=None):
+        """The UNSHARDED stack with the same weights (every rank's slabs all-gathered; for parity checks of the sharded
+        programs): a single-GPU :class:`PackedDecoderStack` on this rank's device.  ``layers``: block indices to keep."""
+        import torch.distributed as dist
+        assert self.world > 1
+
+        def cat(t, dim):
+            raw = t.contiguous().view(torch.uint8)               # (NCCL has no int16: gather the bytes)
+            parts = [torch.empty_like(raw) for _ in range(self.world)]
+            dist.all_gather(parts, raw)
+            return torch.cat([q.view(t.dtype).view(t.shape) for q in parts], dim=dim).contiguous()
+
+        idx = list(range(self.nlayers)) if layers is None else list(layers)
+        twin = PackedDecoderStack.__new__(PackedDecoderStack)
+        twin.model, twin.r, twin.G, twin.device = self.model, self.r, self.G, self.device
+        twin.h, twin.f, twin.kv = self.h, self.f, self.kv
+        twin.nlayers, twin.fused, twin.pdl, twin.batch = len(idx), True, self.pdl, 1
+        twin.rank, twin.world = 0, 1
+        twin.nq, twin.nkv, twin.nf, twin.no = self.h, self.kv, self.f, self.h
+        twin.blocks = []
+        for li in idx:
+            blk, nb = self.blocks[li], {}
+            for name in ("q", "k", "v", "o", "gate", "up", "down"):
+                t = blk[name]
+                nb[name] = {"qweight": cat(t["qweight"], 0), "scales": cat(t["scales"], 1), "scaled_zeros": cat(t["scaled_zeros"], 1),
+                            "N": t["N"] * self.world}
+                if "oweight" in t:
+                    nb[name]["oweight"] = cat(t["oweight"], 0)
+                if t.get("bias") is not None:
+                    nb[name]["bias"] = cat(t["bias"], 0)
+            if self.r > 0:
+                nb["o"]["outlieridx"] = blk["o"]["outlieridx"]
+                nb["o"]["reorder_ids32"] = blk["o"]["reorder_ids32"]
+            twin.blocks.append(nb)
+        twin.x_h, twin.x_f = self.x_h, self.x_f
+        twin.groups = self.groups
+        twin.out, twin.grp_local, twin.grp_full = [], [], []
+        twin.pg = twin.graph = twin.program = None
+        return twin
 
     def enable_allgather(self, process_group):
         """Column-sharded execution: after each launch group, all-gather the ranks' output slices (NCCL over

@@ -379,6 +379,17 @@ class DecodeProgram:
         _lib.check(st, "qeft_decode_program_create")
         self._h = handle
 
+    def set_ranks(self, nranks: int, rank: int, barrier_ptrs: Sequence[int]):
+        """Column-sharded program: ``barrier_ptrs[p]`` = address of rank p's barrier word (uint32, zero, peer-mapped)."""
+        arr = (C.c_void_p * nranks)(*[C.c_void_p(int(a)) for a in barrier_ptrs])
+        _lib.check(_lib.load().qeft_decode_program_set_ranks(self._h, nranks, rank, arr), "qeft_decode_program_set_ranks")
+        self.nranks, self.rank = nranks, rank
+
+    def shard(self, stage: int, part: int, y_full_ptrs: Sequence[int]):
+        """The part's output is this rank's slice of a gathered row: ``y_full_ptrs[p]`` = base of rank p's copy."""
+        arr = (C.c_void_p * len(y_full_ptrs))(*[C.c_void_p(int(a)) for a in y_full_ptrs])
+        _lib.check(_lib.load().qeft_decode_program_shard(self._h, stage, part, arr), "qeft_decode_program_shard")
+
     def run(self, begin: int = 0, end: Optional[int] = None):
         end = self.nstages if end is None else end
         with (_NO_GUARD if self.device.index in (None, torch.cuda.current_device()) else torch.cuda.device(self.device)):

@@ -285,3 +285,87 @@ def test_chained_gathered_input_equals_nccl_chain():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---- decode: the column-sharded chain as ONE persistent launch per rank, all-gathers by data-flow inside the kernel ----
+def _program_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from qeft_b200.decode import PackedDecoderStack
+        st = PackedDecoderStack("7b", layers=3, seed=5, shard=(rank, world), device=f"cuda:{rank}", fast_synth=True)
+        prog = st.enable_sharded_chain_program(dist.group.WORLD)
+        # the unsharded chain on everybody's weights: same arithmetic per output row, so the results are bit-equal
+        twin = st.gathered_twin()
+        twin.enable_chain_program(dataflow=True, ln=st.ln)
+        twin.program.run()
+        torch.cuda.synchronize()
+        ok = True
+        why = ""
+
+        def check(tag):
+            nonlocal ok, why
+            for li in range(st.nlayers):
+                for name in ("q", "k", "v", "h2", "act", "out"):
+                    a, b = st.chain[li][name], twin.chain[li][name]
+                    if not torch.equal(a.view(torch.int16), b.view(torch.int16)):
+                        ok = False
+                        why = why or f"{tag}: block {li} {name}: {(a.float() - b.float()).abs().max().item()}"
+
+        prog.run()
+        torch.cuda.synchronize()
+        dist.barrier()
+        check("eager")
+        for b in st.chain:
+            for v in b.values():
+                v.fill_(float("nan"))
+        torch.cuda.synchronize()
+        dist.barrier()
+        prog.run()
+        prog.run(0, 6)
+        prog.run(6, 12)                  # sub-ranges: the second launch reads gathered rows of the first as plain inputs
+        torch.cuda.synchronize()
+        dist.barrier()
+        check("again + sub-ranges")
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            prog.run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        dist.barrier()
+        with torch.cuda.graph(g):
+            prog.run()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        check("graph replay")
+        q.put((rank, bool(ok), why))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_decode_program_equals_unsharded_chain():
+    """2 ranks: the column-sharded chain program (peer stores from the epilogue, next stage polls its gathered input)
+    gives on every rank exactly the gathered rows of the unsharded chain program on the all-gathered weights: eagerly,
+    run after run, on sub-ranges and under CUDA-graph replay."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_program_worker, args=(rank, world, port, q)) for rank in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True, ""), (1, True, "")], res
