@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--gather", default="program", choices=["program", "fused", "nccl"],
                     help="N > 1: the all-gather fused into the GEMV epilogue (peer stores over NVLink + arrival counters; "
                          "default, measured 11-22 %% faster than NCCL at N = 2 and 4) or one NCCL all-gather per launch group")
     ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the oracle's CPU port even when "
@@ -288,6 +288,40 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def program_parity_check(stack, world, rank):
+    """N > 1, sharded decode program, before the timed loop: one run, then EVERY rank compares the six gathered activation
+    rows of the first and the last decoder block with the UNSHARDED chain program run on that block's all-gathered weights
+    from the same block input (the sharded run's own gathered row): bit-equal (a row's arithmetic does not depend on how
+    the rows are partitioned).  Returns the dict for the JSON line; the caller exits non-zero on a mismatch."""
+    import torch
+    import torch.distributed as dist
+    stack.program.run()
+    torch.cuda.synchronize()
+    dist.barrier()
+    nl = stack.nlayers
+    bad, checked, worst = 0, 0, 0.0
+    for li in sorted({0, nl - 1}):
+        twin = stack.gathered_twin(layers=[li])
+        hidden = stack.x_h if li == 0 else stack.chain[li - 1]["out"].clone()
+        twin.enable_chain_program(dataflow=True, ln=[stack.ln[li]], hidden=hidden)
+        twin.program.run()
+        torch.cuda.synchronize()
+        for name in ("q", "k", "v", "h2", "act", "out"):
+            a, b = stack.chain[li][name], twin.chain[0][name]
+            checked += 1
+            if not torch.equal(a.view(torch.int16), b.view(torch.int16)):
+                bad += 1
+                worst = max(worst, float((a.float() - b.float()).abs().max()))
+        del twin
+        torch.cuda.empty_cache()
+    res = torch.tensor([bad], dtype=torch.int64, device="cuda")
+    dist.all_reduce(res, op=dist.ReduceOp.SUM)
+    return {"groups": checked, "ok": bool(res.item() == 0), "mode": "program", "mismatches_all_ranks": int(res.item()),
+            "max_abs_diff_this_rank": worst,
+            "what": "q, k, v, o+residual, SiLU(gate)*up, down+residual rows of the first and last block, every rank: bit-equal "
+                    "to the unsharded chain program on the all-gathered weights, from the same block input"}
+
+
 def sharded_parity_check(stack, world, rank, gather_mode):
     """N > 1, before the timed loop: one eager step in the active exchange mode, then EVERY rank checks the gathered
     buffer of all four launch groups of the first and of the last decoder block against
@@ -381,6 +415,20 @@ def run_ours(args):
                                shard=(rank, world), batch=args.batch, device=f"cuda:{local}", fast_synth=True)
     gather_mode = args.gather
     if world > 1:
+        if gather_mode == "program" and (args.no_program or args.batch != 1):
+            gather_mode = "fused"
+        if gather_mode == "program":
+            try:
+                # one persistent launch per rank and token, the all-gathers inside the kernel (csrc/decode_w4.cu)
+                stack.enable_sharded_chain_program(dist.group.WORLD)
+                stack.step_eager()
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                print(f"bench.py: sharded decode program unavailable ({type(e).__name__}: {e}); using the fused-gather chain",
+                      file=sys.stderr)
+                stack.program = None
+                stack.chain = None
+                gather_mode = "fused"
         if gather_mode == "fused":
             try:
                 stack.enable_fused_gather(dist.group.WORLD)
@@ -392,13 +440,15 @@ def run_ours(args):
             stack.enable_allgather(dist.group.WORLD)
     parity = None
     if world > 1 and not args.no_parity:
-        parity = sharded_parity_check(stack, world, rank, gather_mode)
+        parity = program_parity_check(stack, world, rank) if gather_mode == "program" else \
+            sharded_parity_check(stack, world, rank, gather_mode)
         if not parity["ok"]:
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_checked": parity,
                                   "error": "gathered outputs differ from the unsharded kernel"}), flush=True)
             os._exit(3)
     use_program = world == 1 and not args.no_program and not args.no_fused and args.batch <= 2
+    sharded_program = world > 1 and gather_mode == "program"
     if use_program:
         try:
             stack.enable_program()   # one persistent cooperative launch per token (csrc/decode_w4.cu)
@@ -568,29 +618,37 @@ def run_ours(args):
                 "workload": (f"llama2-{model} decode b{args.batch}: {workload_layers} decoder blocks x 7 packed QuantLinear "
                              f"(w4 g128 r128) = "
                              + (f"{4 * workload_layers} dependent GEMV stages/token in ONE persistent cooperative launch "
-                                f"(gpu-scope barrier between stages)" if use_program else f"{launches_per_step} GEMV launches/token")
+                                f"(gpu-scope barrier between stages)" if use_program else
+                                (f"{4 * workload_layers} chained stages/token (RMSNorm, SiLU*mul, residual fused; every stage reads "
+                                 f"the previous one's output) in ONE persistent cooperative launch per rank" if sharded_program
+                                 else f"{launches_per_step} GEMV launches/token"))
                              + (f", column-sharded over {world} ranks, all-gather "
-                                + ("fused into the GEMV epilogue (peer stores over NVLink)" if gather_mode == "fused" else "by NCCL")
+                                + ("inside the kernel: the epilogue stores each slice into every rank's gathered row over NVLink, "
+                                   "the next stage polls the elements as they arrive (no collective, fence or counter per stage)"
+                                   if sharded_program else
+                                   ("fused into the GEMV epilogue (peer stores over NVLink)" if gather_mode == "fused" else "by NCCL"))
                                 if world > 1 else "")),
                 "algorithmic_bytes_per_step": int(nbytes_all), "l2_policy": "inputs larger than L2 (3.7 GB of weights streamed per step)",
                 "cuda_graph": workload_graph, "fused_qkv_gateup": workload_fused, "pdl": workload_pdl,
-                "layers": workload_layers, "persistent_program": bool(use_program),
+                "layers": workload_layers, "persistent_program": bool(use_program or sharded_program),
             },
             "decode_tok_s": args.batch * 1e3 / ms_step,
-            "decode_tok_s_note": f"packed linears only ({7 * workload_layers} QuantLinear of the {workload_layers} blocks fed from fixed "
-                                 "activation buffers); attention, norms, embeddings and lm_head are not part of this path (SURVEY.md 8)",
+            "decode_tok_s_note": (f"packed linears only ({7 * workload_layers} QuantLinear of the {workload_layers} blocks"
+                                  + (", chained: each stage reads the previous one's gathered output, o_proj takes the q projection "
+                                     "in place of the attention output" if sharded_program else " fed from fixed activation buffers")
+                                  + "); attention, embeddings and lm_head are not part of this path (SURVEY.md 8)"),
             "clocks": clocks,
             "e2e": {"value": gbs_e2e, "unit": "GB/s", "tok_s": args.batch * 1e3 / (ms_e2e / args.steps),
                     "h2d_bytes_per_step": int(xh.numel() * 2 + xf.numel() * 2), "d2h_bytes_per_step": int(yh.numel() * 2)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
                          "frac_of_nominal_8TBs": per_gpu / 8000.0, "peak_source": peak_src,
-                         "kernel": "decode_w4_kernel" if use_program else "gemv_w4_kernel",
-                         "traffic": ncu_traffic(nbytes_all / world / launches_per_step, "decode" if use_program else "gemv"),
+                         "kernel": "decode_w4_kernel" if (use_program or sharded_program) else "gemv_w4_kernel",
+                         "traffic": ncu_traffic(nbytes_all / world / launches_per_step, "decode" if (use_program or sharded_program) else "gemv"),
                          "traffic_unit": "bytes per launch = traffic_ratio_from_profile x algorithmic bytes of this run's launch "
                                          "(ratio: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full "
                                          "capture of this kernel / its algorithmic bytes; profiles/*_traffic.json)",
-                         "traffic_ratio_from_profile": ncu_traffic(1.0, "decode" if use_program else "gemv"),
+                         "traffic_ratio_from_profile": ncu_traffic(1.0, "decode" if (use_program or sharded_program) else "gemv"),
                          "algorithmic_bytes_per_launch": nbytes_all / world / launches_per_step},
         }
         if parity is not None:

@@ -214,11 +214,6 @@ constexpr unsigned kDfEmpty = 0xFFFFu;
 __device__ __forceinline__ bool d_has_empty(const uint4& v) {
   return (__vcmpeq2(v.x, 0xFFFFFFFFu) | __vcmpeq2(v.y, 0xFFFFFFFFu) | __vcmpeq2(v.z, 0xFFFFFFFFu) | __vcmpeq2(v.w, 0xFFFFFFFFu)) != 0u;
 }
-__device__ __forceinline__ uint4 d_ldrelaxed128_sys(const void* p) {
-  uint4 r;
-  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-  return r;
-}
 __device__ __forceinline__ uint4 d_ldrelaxed128(const void* p) {
   uint4 r;
 #ifdef QEFT_DEC_POLL_CG
@@ -241,27 +236,14 @@ __device__ __forceinline__ void d_strelaxed16(void* p, unsigned short v) {
 #endif
 }
 // 16 bytes of x: polled until every element has arrived when the producer runs in this launch
-// (ns bit 31: the producers are other GPUs -- system-scope loads; the low bits: back-off between two polls)
 __device__ __forceinline__ uint4 d_ldx128(const void* p, bool poll, unsigned ns) {
   if (!poll) return d_ldcg128(p);
-  if (ns & 0x80000000u) {
-    uint4 v = d_ldrelaxed128_sys(p);
-    while (d_has_empty(v)) v = d_ldrelaxed128_sys(p);
-    return v;
-  }
   uint4 v = d_ldrelaxed128(p);
   while (d_has_empty(v)) { __nanosleep(ns); v = d_ldrelaxed128(p); }
   return v;
 }
 __device__ __forceinline__ unsigned short d_ldx16(const void* p, bool poll, unsigned ns) {
   if (!poll) return d_ldcg16(p);
-  if (ns & 0x80000000u) {
-    unsigned short v;
-    do {
-      asm volatile("ld.relaxed.sys.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
-    } while (v == kDfEmpty);
-    return v;
-  }
   unsigned short v = d_ldrelaxed16(p);
   while (v == kDfEmpty) { __nanosleep(ns); v = d_ldrelaxed16(p); }
   return v;
@@ -368,7 +350,10 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
   const int g = lane >> 2, t = lane & 3;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int NS = L.nslots;
-  const unsigned pns = RK.nranks > 1 ? 0x80000000u : (unsigned)L.poll_ns;
+  // (Column-sharded programs poll at gpu scope too: a peer's NVLink stores to THIS GPU's memory are performed in this
+  // GPU's L2, the point of coherence of its HBM, and every element validates itself.  System-scope polling loads were
+  // measured 6 % slower per 70B token at 2 ranks.)
+  const unsigned pns = (unsigned)L.poll_ns;
 
   const uint32_t ring = d_smem_u32(dsm);
   const uint32_t xdig = d_smem_u32(dsm + L.xdig);
@@ -990,19 +975,35 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             const __half res = __ushort_as_half(d_ldx16(S->residual + (size_t)b * Pp->N + n, res_poll, pns));
             h = __hadd(res, h);
           }
-          if (LL) {
-            // a y that later stages of this launch poll: 0xFFFF means "not yet written", so a NaN result is stored as 0x7E00
-            unsigned short hb = __half_as_ushort(h);
-            if ((hb & 0x7FFFu) > 0x7C00u) hb = 0x7E00u;
-            if (Pp->nranks > 1) {
-              // column-sharded: this rank's slice of the gathered row, into every rank's copy (NVLink stores; batch 1)
-              for (int pr = 0; pr < Pp->nranks; ++pr)
-                asm volatile("st.relaxed.sys.global.u16 [%0], %1;" ::"l"(Pp->y_peer[pr] + n), "h"(hb) : "memory");
-            } else {
-              d_strelaxed16(Pp->y + (size_t)b * Pp->N + n, hb);
+          if (!LL) Pp->y[(size_t)b * Pp->N + n] = h;
+        }
+        if (LL) {
+          // a y that later stages of this launch poll: 0xFFFF means "not yet written", so a NaN result is stored as 0x7E00.
+          // Batch 1: the four rows of a qweight row (four adjacent lanes, valid together) leave as ONE 8-byte store --
+          // a quarter of the transactions, which is what matters for the stores that cross NVLink.
+          unsigned hb = (unsigned)__half_as_ushort(h);
+          if ((hb & 0x7FFFu) > 0x7C00u) hb = 0x7E00u;
+          const unsigned h1 = __shfl_down_sync(0xffffffffu, hb, 1), h2 = __shfl_down_sync(0xffffffffu, hb, 2),
+                         h3 = __shfl_down_sync(0xffffffffu, hb, 3);
+          const bool vec = M == 1 && (reinterpret_cast<uintptr_t>(Pp->y) & 7u) == 0;
+          if (valid && vec) {
+            if ((rr & 3) == 0) {
+              const unsigned w0 = hb | (h1 << 16), w1 = h2 | (h3 << 16);
+              if (Pp->nranks > 1) {
+                // column-sharded: this rank's slice of the gathered row, into every rank's copy (NVLink stores)
+                for (int pr = 0; pr < Pp->nranks; ++pr)
+                  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(Pp->y_peer[pr] + n), "r"(w0), "r"(w1) : "memory");
+              } else {
+                asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(Pp->y + n), "r"(w0), "r"(w1) : "memory");
+              }
             }
-          } else {
-            Pp->y[(size_t)b * Pp->N + n] = h;
+          } else if (valid) {
+            if (Pp->nranks > 1) {
+              for (int pr = 0; pr < Pp->nranks; ++pr)
+                asm volatile("st.relaxed.sys.global.u16 [%0], %1;" ::"l"(Pp->y_peer[pr] + n), "h"((unsigned short)hb) : "memory");
+            } else {
+              d_strelaxed16(Pp->y + (size_t)b * Pp->N + n, (unsigned short)hb);
+            }
           }
         }
       }
@@ -1102,14 +1103,25 @@ static int dec_link(DecProgram* p) {
     }
     return n;
   };
-  auto link = [&](const void* ptr, int width, int s, const void*& out_ll, int& out_src) -> int {
-    // the latest earlier stage with a projection whose output buffer is exactly `ptr` ([m, width])
+  auto link = [&](const void* ptr, int width, int s, const void*& out_ll, int& out_src, bool slice_ok) -> int {
+    // the latest earlier stage with a projection whose output buffer is exactly `ptr` ([m, width]); slice_ok (residuals,
+    // which are polled element by element): or, batch 1, contains [ptr, ptr + width) -- a rank's own slice of a gathered row
     for (int ps = s - 1; ps >= 0; --ps) {
       DecStage& pd = p->h_stages[ps];
       const int nout = pd.epilogue == QEFT_EPI_SWIGLU ? 1 : pd.nparts;
       for (int i = 0; i < nout; ++i) {
         DecPart& pp = pd.part[i];
-        if (out_of(pp) != ptr) continue;
+        const char* base = static_cast<const char*>(out_of(pp));
+        const char* q = static_cast<const char*>(ptr);
+        const bool inside = slice_ok && m == 1 && base && q >= base && q + 2 * (size_t)width <= base + 2 * (size_t)width_of(pp);
+        if (out_of(pp) != ptr && !inside) continue;
+        if (inside && writers(out_of(pp)) == 1) {
+          pp.y_ll = out_of(pp);
+          if (s < pp.ll_consumer) pp.ll_consumer = s;
+          out_ll = out_of(pp);
+          out_src = ps;
+          return 1;
+        }
         if (width_of(pp) != width || writers(ptr) != 1) return -1;   // produced in the program, but not linkable: barrier
         pp.y_ll = ptr;
         if (s < pp.ll_consumer) pp.ll_consumer = s;
@@ -1124,9 +1136,9 @@ static int dec_link(DecProgram* p) {
   if (p->ll_env) {
     for (int s = 1; s < nstages; ++s) {
       DecStage& d = p->h_stages[s];
-      const int rx = link(d.x, d.K, s, d.x_ll, d.x_src);
+      const int rx = link(d.x, d.K, s, d.x_ll, d.x_src, false);
       int rr = 0;
-      if (d.residual) rr = link(d.residual, d.part[0].N, s, d.res_ll, d.res_src);
+      if (d.residual) rr = link(d.residual, d.part[0].N, s, d.res_ll, d.res_src, true);
       if (rx < 0 || rr < 0) d.force_barrier = 1;
     }
     for (int s = 0; s + 1 < nstages; ++s) {

@@ -109,7 +109,7 @@ class PackedDecoderStack:
         by gpu-scope barriers (``QEFT_DECODE_LL=0``).  Same weights and weight bytes
         as :meth:`enable_program`."""
         import os
-        assert self.world == 1 and self.fused and self.kv == self.h
+        assert self.world == 1 and self.fused
         m, dev = self.batch, self.device
         g = torch.Generator(device=dev)
         g.manual_seed(4242)

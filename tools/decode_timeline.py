@@ -24,6 +24,11 @@ def main():
     for _ in range(5):
         st.step_eager()
     torch.cuda.synchronize()
+    print(json.dumps(collect(prog)))
+
+
+def collect(prog):
+    """Summary of the stamps of the program's last run (QEFT_DECODE_STAMPS=1 must have been set before the first run)."""
     n = prog.nstages
     buf = np.zeros((n * (32 + 640) + 24,), dtype=np.uint64)
     lib = _lib.load()
@@ -76,7 +81,7 @@ def main():
         out["cta0_" + nm] = {"wait_cycles": int(e[0]), "math_cycles": int(e[1]), "issue_cycles": int(e[2]),
                              "block_period_cycles_sum": int(e[3]), "issues": int(e[4]), "blocks_waited": int(e[5]),
                              "blocks": int(e[6])}
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
