@@ -115,7 +115,11 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
   } else if (warp >= 4) {
     // ================= dequant warps: one packed chunk (row n, 32 features) per thread and k-block =================
     const int dt = tid - 128;                 // 0..511
-    const int nl = dt >> 3, kc = dt & 7;      // row within the k-block, 32-feature chunk within the tile
+    // row nl within the k-block, 32-feature chunk kc within the tile.  A quarter-warp (8 lanes = one wavefront of the
+    // 16-byte shared-memory stores below) is {both halves of a 64-feature chunk} x {the 4 rows of one qweight row}: its
+    // stores fall into 8 different 16-byte bank groups (the swizzle XORs the row into the chunk index) and its loads are
+    // one whole 128-byte packed tile.  (Round 1 put the 8 chunks of one row there: 4-way bank conflicts, 19 M per launch.)
+    const int kc = (dt & 1) | (((dt >> 3) & 3) << 1), nl = ((dt >> 1) & 3) | ((dt >> 5) << 2);
     const int kf = kf0 + 32 * kc;             // first feature of this thread's chunk
     const bool live = kf < p.K;
     const bool outl = live && p.ow != nullptr && kf >= p.K - p.r;
