@@ -667,12 +667,9 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       dec_stamp<DBG>(L, s, 4);
       // the reference's two roundings: (x * rs).to(fp16), then * weight in fp16
       auto normed = [&](float v, int col, float rs) { return __half2float(__hmul(nw[col], __float2half_rn(v * rs))); };
-      for (int q = 0; q < npass; ++q) {
-        const int it = q * kDThreads + tid;
-        uint4 v0; int b, st; bool live;
-        if (q == 0) { v0 = k0a; b = kb0; st = ks0; live = kl0; }
-        else if (q == 1) { v0 = k1a; b = kb1; st = ks1; live = kl1; }
-        else load_item(it, v0, b, st, live);
+      // one pass = one item per thread; the passes go in PAIRS (both loads first, then two independent conversion chains
+      // that the scheduler interleaves: a pass alone is a chain of ~20 dependent shuffles and is latency-bound)
+      auto digit_pass = [&](int it, uint4 v0, int b, int st, bool live) {
         const bool valid = it < nitems;
         const int sub = it & 15, tt = sub >> 2, half = (sub >> 1) & 1, hs = sub & 1;
         const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
@@ -750,6 +747,22 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
             const float cg = e > -100 ? __uint_as_float((uint32_t)(127 + e - 22 - 4) << 23) : 0.f;
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xsum + (uint32_t)(st * 16 + b * 8)), "f"(sum), "f"(cg) : "memory");
           }
+        }
+      };
+      for (int q = 0; q < npass; q += 2) {
+        uint4 va, vb; int ba, bb, sa, sb; bool la, lb;
+        if (q == 0) {
+          va = k0a; ba = kb0; sa = ks0; la = kl0;
+          vb = k1a; bb = kb1; sb = ks1; lb = kl1;
+        } else {
+          load_item(q * kDThreads + tid, va, ba, sa, la);
+          load_item((q + 1) * kDThreads + tid, vb, bb, sb, lb);
+        }
+        if (q + 1 < npass) {
+          digit_pass(q * kDThreads + tid, va, ba, sa, la);
+          digit_pass((q + 1) * kDThreads + tid, vb, bb, sb, lb);
+        } else {
+          digit_pass(q * kDThreads + tid, va, ba, sa, la);
         }
       }
       dec_stamp<DBG>(L, s, 6);
