@@ -1045,7 +1045,8 @@ struct DecProgram {
   unsigned long long* d_stamps = nullptr;
   DecReset* d_resets = nullptr;
   int nresets = 0;
-  int ll_env = 1;
+  int ll_env = -1;              // QEFT_DECODE_LL at creation: 1 / 0 = data-flow ordering on / off, unset = only for sharded programs
+  bool use_ll = false;
   bool dirty = false;           // the description changed since the last upload (qeft_decode_program_shard)
   DecRanks ranks = {};          // column-sharded programs: the ranks' barrier counters
   std::vector<void*> side_tables;
@@ -1095,7 +1096,8 @@ static int dec_launch(const DecProgram* p, int s0, int s1, const DecLayout& L, s
 // Data-flow links: a stage whose x (or residual) IS the y of an earlier stage's projection polls that buffer instead of
 // waiting at a barrier (the kernel's "data-flow by sentinel").  Only a buffer written by exactly ONE projection of the
 // program can be a flag for itself: anything else (a scratch buffer reused by several stages, a width mismatch) makes
-// the consuming stage wait at a barrier.  QEFT_DECODE_LL=0 turns data-flow off.  For a column-sharded projection
+// the consuming stage wait at a barrier.  On one GPU barriers are faster, so data-flow is used by default
+// only by column-sharded programs, where it IS the exchange; QEFT_DECODE_LL=1 / 0 at creation forces it on / off.  For a column-sharded projection
 // (qeft_decode_program_shard) "the y" is the local copy of the gathered row.  Recomputed and uploaded whenever the
 // program's description changes.
 static int dec_link(DecProgram* p) {
@@ -1146,7 +1148,8 @@ static int dec_link(DecProgram* p) {
     return 0;                                                   // not produced by this program: external input
   };
   std::vector<DecReset> resets;
-  if (p->ll_env) {
+  p->use_ll = p->ll_env == 1 || (p->ll_env < 0 && p->ranks.nranks > 1);
+  if (p->use_ll) {
     for (int s = 1; s < nstages; ++s) {
       DecStage& d = p->h_stages[s];
       const int rx = link(d.x, d.K, s, d.x_ll, d.x_src, false);
@@ -1276,7 +1279,7 @@ extern "C" int qeft_decode_program_create(const qeft_decode_stage_t* stages, int
   cudaError_t e = cudaMalloc(&p->d_stages, sizeof(DecStage) * (size_t)nstages);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_sync, 256);
   if (e == cudaSuccess) e = cudaMemset(p->d_sync, 0, 256);
-  p->ll_env = dec_env_int("QEFT_DECODE_LL", 1);             // (read at every creation: tests build both kinds of program)
+  p->ll_env = dec_env_int("QEFT_DECODE_LL", -1);            // (read at every creation: tests build both kinds of program)
   if (e == cudaSuccess) e = (cudaError_t)dec_link(p);
   if (e != cudaSuccess) {
     if (p->d_stages) cudaFree(p->d_stages);
@@ -1322,6 +1325,7 @@ extern "C" int qeft_decode_program_set_ranks(qeft_decode_program_t* prog, int nr
     if (!barrier_peer[i]) return QEFT_E_NULL;
     p->ranks.bar_peer[i] = static_cast<unsigned*>(barrier_peer[i]);
   }
+  p->dirty = true;
   return QEFT_OK;
 }
 
@@ -1424,7 +1428,7 @@ extern "C" int qeft_decode_program_run(qeft_decode_program_t* prog, int stage_be
     if (d.res_ll != nullptr && d.res_src >= stage_begin) uses_ll = 1;
   }
   const bool sharded = p->ranks.nranks > 1;
-  if (sharded && !p->ll_env) return QEFT_E_UNSUPPORTED;      // the exchange between ranks IS the data-flow protocol
+  if (sharded && !p->use_ll) return QEFT_E_UNSUPPORTED;      // the exchange between ranks IS the data-flow protocol
   if (uses_ll) nbar_total += sharded ? 2 : 1;                // the barrier after re-arming the data-flow outputs
   if (sharded) nbar_total += 2;                              // the rank barrier that ends the launch
   const bool instrumented = stamps_env != 0 || debug_env != 0;
