@@ -76,6 +76,9 @@ def _prefill_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
+    # the test is about the exchange being exact: every launch here must add its k-blocks in the same order, so the
+    # split-K configurations of the plain GEMM (few tiles at M = 300; the gather launches never split) are switched off
+    os.environ["QEFT_GEMM_SMALLM"] = "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
