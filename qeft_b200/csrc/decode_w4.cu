@@ -549,9 +549,25 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
     // no barrier.  Every other stage after the first waits until all CTAs have stored their rows of the previous one.
     // (The descriptor copy of stage s was written before the previous stage's post-consume barrier.)
     const bool ll_x = LL && S->x_ll != nullptr && S->x_src >= s_begin && !S->force_barrier;
+    const int K = S->K, r = S->r, ns = S->nsteps;
+    // o_proj's gather indices of this thread's first staging item (and of its outlier activations) do not depend on x:
+    // they are loaded BEFORE the barrier, like the weights (one L2 round trip less on the boundary's critical path)
+    int4 gi0 = make_int4(0, 0, 0, 0), gi1 = gi0, go0 = gi0, go1 = gi0;
+    if (S->gather != nullptr) {
+      const int sb = tid >> 4, b = sb / ns, st = sb - b * ns, k0 = st * 128 + (tid & 15) * 8;
+      if (tid < M * ns * 16 && k0 < S->nchunks * 32) {
+        gi0 = __ldg(reinterpret_cast<const int4*>(S->gather + k0));
+        gi1 = __ldg(reinterpret_cast<const int4*>(S->gather + k0 + 4));
+      }
+      const int xt = kDThreads - 1 - tid;
+      if (xt < M * (r >> 3)) {
+        const int jj = xt % (r >> 3);
+        go0 = __ldg(reinterpret_cast<const int4*>(S->gather + K - r + 8 * jj));
+        go1 = __ldg(reinterpret_cast<const int4*>(S->gather + K - r + 8 * jj + 4));
+      }
+    }
     if (s > s_begin && !ll_x) barrier_wait();
     const DecTiles R = dec_tiles(S, cta, ncta);
-    const int K = S->K, r = S->r, ns = S->nsteps;
 
     dec_stamp<DBG>(L, s, 0);
     // ---- x: block fixed point per 128-column step, signed-byte digits ------------------------------------------------
@@ -565,7 +581,11 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
       const __half* xg = S->x;
       // o_proj's gather (qlinear.py:275): copy x to shared memory first (coalesced, one L2 round trip; the buffer aliases
       // the partial-sum slices, idle between two stages), then gather from there instead of 16 scattered 2-byte L2 loads
+#ifdef QEFT_DEC_LEAN_EXPERIMENT
+      const bool xraw_ok = false;
+#else
       const bool xraw_ok = S->gather != nullptr && (size_t)M * (size_t)K * 2 <= (size_t)L.part_bytes;
+#endif
       const uint32_t xraw = d_smem_u32(dsm + L.part);
       if (xraw_ok) {
         // (without a barrier in front of this stage, warps may still be adding the previous stage's slices)
@@ -585,8 +605,13 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         }
         return d_ldx16(row + col, ll_x, pns);
       };
+#ifdef QEFT_DEC_LEAN_EXPERIMENT   // (code-size experiment: no gather, no norm -- results are wrong for stages that have them)
+      const int32_t* const gat = nullptr;
+      const __half* const nw = nullptr;
+#else
       const int32_t* gat = S->gather;
       const __half* nw = S->norm_w;
+#endif
       const int live_k = S->nchunks * 32;
       const int nitems = M * ns * 16;
       const int npass = (nitems + kDThreads - 1) / kDThreads;
@@ -603,7 +628,11 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         if (live) {
           const __half* xr = xg + (size_t)b * K;
           if (gat) {
-            const int4 i0 = __ldg(reinterpret_cast<const int4*>(gat + k0)), i1 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 4));
+            int4 i0 = gi0, i1 = gi1;                           // (the first pass's indices were loaded before the barrier)
+            if (it != tid) {
+              i0 = __ldg(reinterpret_cast<const int4*>(gat + k0));
+              i1 = __ldg(reinterpret_cast<const int4*>(gat + k0 + 4));
+            }
             auto pk = [&](int a, int c) { return (uint32_t)ldx16(xr, b, a) | ((uint32_t)ldx16(xr, b, c) << 16); };
             v0 = make_uint4(pk(i0.x, i0.y), pk(i0.z, i0.w), pk(i1.x, i1.y), pk(i1.z, i1.w));
           } else {
@@ -624,7 +653,7 @@ decode_w4_kernel(const DecStage* __restrict__ stages, int s_begin, int s_end, un
         const int b = xo_tid / (r >> 3), jj = xo_tid - b * (r >> 3);
         const __half* xr = xg + (size_t)b * K;
         if (gat) {
-          const int4 a = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj)), c = __ldg(reinterpret_cast<const int4*>(gat + K - r + 8 * jj + 4));
+          const int4 a = go0, c = go1;
           auto pk = [&](int i0, int i1) { return (uint32_t)ldx16(xr, b, i0) | ((uint32_t)ldx16(xr, b, i1) << 16); };
           xo_v = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(c.x, c.y), pk(c.z, c.w));
         } else {
