@@ -112,7 +112,7 @@ QEFT_API int qeft_gemv_w4_multi(const void* x, const qeft_gemv_part_t* parts, in
  * `*epoch * nranks * QEFT_ARRIVALS_PER_LAUNCH` before it reads its input; with QEFT_F_PDL that counter is the ONLY
  * ordering between the two launches (no grid-completion wait), so the chain never pays a kernel boundary.
  * `epoch` is a device-resident step counter the caller increments once per decode step (graph-replay friendly).
- * `local_count` is reserved.  x_gather, when given, must be 16-byte aligned.
+ * x_gather, when given, must be 16-byte aligned.
  * A launch with `wait_flag` reads x through L2 (coherent loads), never through the read-only path.
  * Contract of QEFT_F_PDL for every entry point: only x (and y as a reused buffer) are ordered after the previous
  * kernel in the stream; the packed tensors (qweight, scales, scaled_zeros, oweight, bias) are prefetched BEFORE the
@@ -126,7 +126,6 @@ typedef struct {
   int y_ld;                                            /* elements between batch rows of the gathered buffers */
   void* y_peer[QEFT_MAX_RANKS][QEFT_GEMV_MAX_PARTS];   /* rank p's buffer for part i, offset to THIS rank's columns */
   uint32_t* done_peer[QEFT_MAX_RANKS];                 /* rank p's arrival counter of this launch */
-  uint32_t* local_count;                               /* reserved, must be NULL (never read) */
   const uint32_t* wait_flag;                           /* local arrival counter of the launch depended on, or NULL */
   const uint32_t* epoch;
   /* qeft_gemm_w4_gather only, optional: the MULTICAST mapping (NVLS; torch symmetric memory's multicast_ptr) of the

@@ -29,7 +29,7 @@ class Gather(C.Structure):
     _fields_ = [("nranks", C.c_int), ("y_ld", C.c_int),
                 ("y_peer", (C.c_void_p * GEMV_MAX_PARTS) * MAX_RANKS),
                 ("done_peer", C.c_void_p * MAX_RANKS),
-                ("local_count", C.c_void_p), ("wait_flag", C.c_void_p), ("epoch", C.c_void_p),
+                ("wait_flag", C.c_void_p), ("epoch", C.c_void_p),
                 ("y_mc", C.c_void_p * GEMV_MAX_PARTS)]
 
 

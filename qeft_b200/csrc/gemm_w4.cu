@@ -12,15 +12,18 @@
 //     64 columns per k-block), turn them into fp16 with the lop3 magic-number trick + one HFMA2 per pair
 //     (w = fma(q, s, sz), the reference's single rounding) and write them with tcgen05.st.  Dequantised weights
 //     never touch shared memory, so shared-memory bandwidth is left to the activation tiles.
-//   * The ACTIVATIONS are the B operand (N_umma = 128 tokens): 128 x 64 fp16 tiles, K-major, 128-byte swizzle,
-//     brought in by TMA (cp.async.bulk.tensor) into a 6-stage ring.
-//   * One CTA computes 256 features x 128 tokens: two fp32 accumulators of 128 TMEM columns each (y^T tiles),
-//     so one activation tile feeds two MMAs (halves the L2 -> SM activation traffic).
+//   * The ACTIVATIONS are the B operand (N_umma = BN tokens): BN x 64 fp16 tiles, K-major, 128-byte swizzle,
+//     brought in by TMA (cp.async.bulk.tensor) into a ring of stages of two k-blocks.
+//   * One CTA computes 128 features x BN tokens (BN = 256; 64 / 128 for small M): one fp32 accumulator of BN TMEM
+//     columns (y^T tile) + a ring of weight blocks in the remaining columns.
 //   * The dense fp16 outlier columns are simply the last r/64 k-blocks: same pipeline, the dequant warps copy
 //     oweight[f, 64 b .. 64 b + 63] to TMEM unchanged; the dead int4 columns K-r..K-1 are never read.
-//   * Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane, tcgen05.commit to
-//     mbarriers), warp 2 TMEM allocator, warps 4-19 dequant (two sets of 8 warps that alternate k-blocks; in a
-//     set one warpgroup per 128-feature block) and then epilogue (tcgen05.ld, + bias, fp16, transposed through shared memory, 16-byte stores).
+//   * Warp roles (512 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane, tcgen05.commit to
+//     mbarriers), warp 2 TMEM allocator, warps 4-15 dequant (three sets of 4 warps that alternate ring stages of two
+//     k-blocks; a warp owns 32 features = its TMEM lane quadrant) and then epilogue (tcgen05.ld, + bias, fp16, transposed
+//     through shared memory, 16-byte stores; split-K launches: fp32 partials + last-arriver reduction).
+//   * Not instantiated: two feature blocks per CTA (NRB = 2, 16 dequant warps) and three k-blocks per ring stage
+//     (KPS = 3): both ended in unspecified launch failures in round 1 and were not diagnosed.
 #include "tc_common.cuh"
 
 #include <stdlib.h>
@@ -80,7 +83,6 @@ struct GemmParams {
   __half* y_peer[QEFT_MAX_RANKS];
   __half* y_mc;            // multicast mapping of the gathered buffer (one store reaches every rank), or null
   uint32_t* done_peer[QEFT_MAX_RANKS];
-  uint32_t* local_count;
   const uint32_t* wait_flag;
   const uint32_t* epoch;
   // split-K (small M: gridDim.z CTAs share a tile, each over a contiguous range of ring stages): fp32 partial tiles
@@ -627,7 +629,6 @@ static int gemm_entry(const void* x, const void* qweight, const void* scales, co
       prm.y_peer[pr] = static_cast<__half*>(gat->y_peer[pr][0]);
       prm.done_peer[pr] = gat->done_peer[pr];
     }
-    prm.local_count = gat->local_count;
     prm.wait_flag = gat->wait_flag;
     prm.epoch = gat->epoch;
   }

@@ -72,7 +72,6 @@ struct GemvParams {
   int y_ld;
   __half* y_peer[QEFT_MAX_RANKS][QEFT_GEMV_MAX_PARTS];
   uint32_t* done_peer[QEFT_MAX_RANKS];
-  uint32_t* local_count;
   const uint32_t* wait_flag;
   int flag_only;          // 1: the arrival counter alone orders this launch after its input (no grid-completion wait)
   const uint32_t* epoch;
@@ -1059,7 +1058,6 @@ static int gemv_entry(const void* x, const qeft_gemv_part_t* parts, int nparts, 
         prm.y_peer[pr][i] = static_cast<__half*>(gat->y_peer[pr][i]);
       }
     }
-    prm.local_count = gat->local_count;
     prm.wait_flag = gat->wait_flag;
     static const int gridwait_env = getenv("QEFT_GATHER_GRIDWAIT") ? atoi(getenv("QEFT_GATHER_GRIDWAIT")) : 0;
     prm.flag_only = (gat->wait_flag != nullptr && (flags & QEFT_F_PDL) && !gridwait_env) ? 1 : 0;

@@ -301,7 +301,6 @@ class PackedDecoderStack:
                         g.y_peer[pr][i] = base + 2 * col
                         col += self.blocks[li][n]["N"]
                     g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * li_flat
-                g.local_count = None
                 g.wait_flag = prev_flag
                 g.epoch = self.epoch.data_ptr()
                 prev_flag = buf.data_ptr() + 4 * li_flat

@@ -108,7 +108,6 @@ class PackedPrefillStack:
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if multicast else 0
         self.multicast = bool(mc)
         self.epoch = torch.zeros((1,), dtype=torch.int32, device=self.device)
-        self.local_counts = torch.zeros((nlaunch,), dtype=torch.int32, device=self.device)
         offs, off = [], flag_bytes
         self.y_full = []
         for s in range(2):
@@ -131,7 +130,6 @@ class PackedPrefillStack:
                     g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * li_flat
                 if mc:
                     g.y_mc[0] = mc + offs[li % 2][n] + 2 * self.rank * (w // P)
-                g.local_count = self.local_counts.data_ptr() + 4 * li_flat
                 g.wait_flag = prev_flag
                 g.epoch = self.epoch.data_ptr()
                 prev_flag = buf.data_ptr() + 4 * li_flat

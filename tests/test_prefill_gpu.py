@@ -22,7 +22,6 @@ def test_gemm_gather_single_rank_writes_pitched_columns():
     g.nranks, g.y_ld = 1, W
     g.y_peer[0][0] = full.data_ptr() + 2 * 256           # columns 256 .. 511
     g.done_peer[0] = flags.data_ptr()
-    g.local_count = flags.data_ptr() + 4
     g.wait_flag = None
     g.epoch = epoch.data_ptr()
     T = {k: d(L[k]) for k in ("qweight", "scales", "scaled_zeros", "oweight", "bias")}
@@ -41,7 +40,6 @@ def test_gemm_gather_single_rank_writes_pitched_columns():
     g2.y_peer[0][0] = full.data_ptr()
     flags2 = torch.zeros(2, dtype=torch.int32, device="cuda")
     g2.done_peer[0] = flags2.data_ptr()
-    g2.local_count = flags2.data_ptr() + 4
     g2.wait_flag = flags.data_ptr()
     g2.epoch = epoch.data_ptr()
     qeft_cuda.gemm_w4_gather(d(x), T["qweight"], T["scales"], T["scaled_zeros"], T["oweight"], T["bias"], g2)

@@ -228,7 +228,6 @@ def _chain_worker(rank, world, port, q):
             for pr in range(world):
                 g.y_peer[pr][0] = hdl.buffer_ptrs[pr] + off + 2 * rank * w
                 g.done_peer[pr] = hdl.buffer_ptrs[pr] + 4 * i
-            g.local_count = None
             g.wait_flag = prev
             g.epoch = epoch.data_ptr()
             prev = buf.data_ptr() + 4 * i
