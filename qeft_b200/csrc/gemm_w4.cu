@@ -89,6 +89,7 @@ struct GemmParams {
   // [split][M][N] and one arrival counter per tile; the CTA that arrives last adds the partials in split order
   float* ws;
   unsigned* counters;
+  int stream_k;            // one CTA per SM, each a contiguous range of the launch's (tile, stage) units
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row groups 1024
@@ -106,42 +107,82 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor (Cfg::kIdesc): D = F32, A = B = F16, both K-major, M = 128, N = BN
 // MC: clusters of two CTAs (adjacent feature blocks, same tokens) share every activation tile: each CTA loads one
 // half with a multicast TMA, both receive the whole tile -- halves the L2 -> SM activation traffic.
+//
+// Work of a CTA = a list of SEGMENTS (tile, range of ring stages), walked in lock step by all warp roles:
+//   * plain launch: one segment, the whole tile of blockIdx.(x, y);
+//   * split-K (gridDim.z > 1): one segment, the blockIdx.z-th part of the tile's stages;
+//   * stream-K (p.stream_k; one CTA per SM): the launch's (tile, stage) units, tile-major, are cut into gridDim.x equal
+//     contiguous ranges, so every SM finishes at the same time whatever the number of tiles (256 tiles on 148 SMs are
+//     1.73 units per CTA instead of two waves); a range covers the tail of one tile, whole tiles, and the head of another.
+// A tile whose stages are shared by several segments is reduced through fp32 partial tiles in a workspace: the segment
+// that arrives LAST at the tile's counter adds the partials in part order (deterministic), adds the bias and stores.
+// TMEM, barriers and the tensor map are set up once per CTA; ring stages and barrier phases run on across segments.
+struct GemmSeg { int tok0, n0, tile, sb, se, parts, part; };
+
 template <int NRB, int BN, bool MC, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   using Cfg = GemmCfg<NRB, BN>;
-  constexpr int kBM = Cfg::kBM, kBN = Cfg::kBN, kXStages = Cfg::kXStages, kAStages = Cfg::kAStages;
+  static_assert(NRB == 1, "one 128-feature block per CTA");
+  constexpr int kBN = Cfg::kBN, kXStages = Cfg::kXStages, kAStages = Cfg::kAStages;
   constexpr int kXStageBytes = Cfg::kXStageBytes, kTmemA0 = Cfg::kTmemA0, kDequantSets = Cfg::kSets;
   constexpr int kKPS = Cfg::kKPS, kXTileBytes = Cfg::kXTileBytes;
   constexpr uint32_t kIdesc = BF16 ? Cfg::kIdescBF16 : Cfg::kIdescF16;
+  constexpr int rb = 0, nrb = 1;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kXStages + 1];
+  __shared__ __align__(8) uint64_t bars[2 * kXStages + 2];
   __shared__ uint32_t s_tmem_base;
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t xs0 = (smem_addr(smem_raw) + 1023u) & ~1023u;          // 1024-byte aligned stage ring
-  uint8_t* xs_gen = smem_raw + (xs0 - smem_addr(smem_raw));
+  // epilogue staging (2 KB per dequant warp) BEHIND the ring: the producer may already be loading the next segment's
+  // activation tiles into the ring while a segment's accumulator is drained
+  uint8_t* stage_gen = smem_raw + (xs0 - smem_addr(smem_raw)) + (size_t)kXStages * kXStageBytes;
   const uint32_t bar0 = smem_addr(bars);
   auto x_full = [&](int s) { return bar0 + 8 * s; };               // TMA bytes + the dequant warps' arrivals
   auto x_empty = [&](int s) { return bar0 + 8 * (kXStages + s); };  // tcgen05.commit of the k-block's MMAs
   auto a_full = x_full;
   auto a_empty = x_empty;
-  const uint32_t acc_full = bar0 + 8 * (2 * kXStages);
+  const uint32_t acc_full = bar0 + 8 * (2 * kXStages);             // a segment's MMAs are done
+  const uint32_t acc_empty = acc_full + 8;                         // ... and its accumulator has been read (12 warps)
 
-  const int tok0 = blockIdx.x * kBN;
-  const int n0 = blockIdx.y * kBM;
-  const int nrb = (p.N - n0) >= kBM ? NRB : (p.N - n0) / 128;   // 128-feature blocks of this tile (N % 128 == 0)
-  // split-K: this CTA's contiguous range of ring stages [st0, st0 + nst) = k-blocks [kb0, nkb)
-  const int nsplit = (int)gridDim.z, split = (int)blockIdx.z;
-  const int nst_all = (p.nkb + Cfg::kKPS - 1) / Cfg::kKPS;
-  const int st0 = (int)(((long long)nst_all * split) / nsplit), st1 = (int)(((long long)nst_all * (split + 1)) / nsplit);
-  const int nst = st1 - st0;                             // ring stages of this CTA
-  const int kb0 = st0 * Cfg::kKPS;
-  const int nkb = min(p.nkb, st1 * Cfg::kKPS);           // (one past) this CTA's last k-block
+  const int nst_all = (p.nkb + kKPS - 1) / kKPS;                   // ring stages of a whole tile
+  const int FB = p.N / 128;                                        // feature blocks
+  // this CTA's range of (tile, stage) units [u_cur, u_end)
+  int u_begin, u_end;            // (units fit 32 bits: at most 8192 tiles x a few hundred stages, times the grid)
+  if (p.stream_k) {
+    const int U = cdiv(p.M, kBN) * FB * nst_all;
+    u_begin = (int)(((long long)U * blockIdx.x) / gridDim.x);
+    u_end = (int)(((long long)U * (blockIdx.x + 1)) / gridDim.x);
+  } else {
+    const int nsplit = (int)gridDim.z, split = (int)blockIdx.z;
+    const int t0 = ((int)blockIdx.x * FB + (int)blockIdx.y) * nst_all;
+    u_begin = t0 + (nst_all * split) / nsplit;
+    u_end = t0 + (nst_all * (split + 1)) / nsplit;
+  }
+  // segment that starts at unit u (tile ids are token-tile major: CTAs that run together share activation tiles in L2)
+  auto seg_at = [&](int u) {
+    GemmSeg g;
+    g.tile = u / nst_all;
+    g.sb = u - g.tile * nst_all;
+    const int left = u_end - u;
+    g.se = left < nst_all - g.sb ? g.sb + left : nst_all;
+    g.tok0 = (g.tile / FB) * kBN;
+    g.n0 = (g.tile % FB) * 128;
+    if (p.stream_k) {            // (a range is at least one tile long: a tile is shared by at most two CTAs)
+      g.parts = (g.sb == 0 && g.se == nst_all) ? 1 : 2;
+      g.part = g.sb > 0 ? 1 : 0;
+    } else {
+      g.parts = (int)gridDim.z;
+      g.part = (int)blockIdx.z;
+    }
+    return g;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < kXStages; ++s) { mbar_init(x_full(s), 1 + 4 * nrb); mbar_init(x_empty(s), MC ? 2 : 1); }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kDequantWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -172,60 +213,79 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         } while ((int)(got - want) < 0);
         asm volatile("fence.proxy.async;" ::: "memory");
       }
-      for (int st = 0; st < nst; ++st) {
-        const int s = st % kXStages, use = st / kXStages;
-        if (use > 0) mbar_wait(x_empty(s), (uint32_t)((use - 1) & 1));
-        const int nblk = min(kKPS, nkb - (kb0 + st * kKPS));
-        if (p.dbg & 2) { mbar_arrive(x_full(s)); continue; }
-        mbar_expect_tx(x_full(s), (uint32_t)(nblk * kXTileBytes));
-        for (int j = 0; j < nblk; ++j) {
-          const int kb = kb0 + st * kKPS + j;
-          const int k0 = kb < p.nkb_q ? kb * kBK : p.K - p.r + (kb - p.nkb_q) * kBK;
-          const uint32_t dst = xs0 + s * kXStageBytes + j * kXTileBytes;
-          if (MC)     // my half of the tokens, to both CTAs (the peer sends the other half)
-            tma_load_2d_mc(dst + crank * (kXTileBytes / 2), &xmap, k0, tok0 + (int)crank * (kBN / 2), x_full(s), (uint16_t)3);
-          else
-            tma_load_2d(dst, &xmap, k0, tok0, x_full(s));
+      int rit = 0;                                  // ring iteration: stages issued so far by this CTA
+      for (int u = u_begin; u < u_end;) {
+        const GemmSeg g = seg_at(u);
+        for (int st = g.sb; st < g.se; ++st, ++rit) {
+          const int s = rit % kXStages, use = rit / kXStages;
+          if (use > 0) mbar_wait(x_empty(s), (uint32_t)((use - 1) & 1));
+          const int nblk = min(kKPS, p.nkb - st * kKPS);
+          if (p.dbg & 2) { mbar_arrive(x_full(s)); continue; }
+          mbar_expect_tx(x_full(s), (uint32_t)(nblk * kXTileBytes));
+          for (int j = 0; j < nblk; ++j) {
+            const int kb = st * kKPS + j;
+            const int k0 = kb < p.nkb_q ? kb * kBK : p.K - p.r + (kb - p.nkb_q) * kBK;
+            const uint32_t dst = xs0 + s * kXStageBytes + j * kXTileBytes;
+            if (MC)     // my half of the tokens, to both CTAs (the peer sends the other half)
+              tma_load_2d_mc(dst + crank * (kXTileBytes / 2), &xmap, k0, g.tok0 + (int)crank * (kBN / 2), x_full(s), (uint16_t)3);
+            else
+              tma_load_2d(dst, &xmap, k0, g.tok0, x_full(s));
+          }
         }
+        u += g.se - g.sb;
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      for (int st = 0; st < nst; ++st) {
-        const int s = st % kXStages;
-        mbar_wait(x_full(s), (uint32_t)((st / kXStages) & 1));
-        tc_fence_after();
-        const int nblk = min(kKPS, nkb - (kb0 + st * kKPS));
-        for (int j = 0; j < nblk; ++j) {
-#pragma unroll
-          for (int k16 = 0; k16 < kBK / 16; ++k16) {
-            const uint64_t bdesc = make_b_desc(xs0 + s * kXStageBytes + j * kXTileBytes + k16 * 32);
-            for (int rb = 0; rb < nrb; ++rb)
-              umma_ts_f16(tmem + kBN * rb, tmem + kTmemA0 + Cfg::kAStageCols * s + Cfg::kABlockCols * j + 32 * rb + 8 * k16,
-                          bdesc, kIdesc, (uint32_t)((st | j | k16) != 0));
-          }
+      int rit = 0, seg = 0;
+      for (int u = u_begin; u < u_end; ++seg) {
+        const GemmSeg g = seg_at(u);
+        if (seg > 0) {                // the previous segment's accumulator has been read by all epilogue warps
+          mbar_wait(acc_empty, (uint32_t)((seg - 1) & 1));
+          tc_fence_after();
         }
-        if (MC) tc_commit_mc(x_empty(s), (uint16_t)3);   // the stage is rewritten by BOTH CTAs' producers
-        else tc_commit(x_empty(s));     // the stage (smem tiles + TMEM blocks) is free once these MMAs have read it
+        for (int st = g.sb; st < g.se; ++st, ++rit) {
+          const int s = rit % kXStages;
+          mbar_wait(x_full(s), (uint32_t)((rit / kXStages) & 1));
+          tc_fence_after();
+          const int nblk = min(kKPS, p.nkb - st * kKPS);
+          for (int j = 0; j < nblk; ++j) {
+#pragma unroll
+            for (int k16 = 0; k16 < kBK / 16; ++k16) {
+              const uint64_t bdesc = make_b_desc(xs0 + s * kXStageBytes + j * kXTileBytes + k16 * 32);
+              umma_ts_f16(tmem + kBN * rb, tmem + kTmemA0 + Cfg::kAStageCols * s + Cfg::kABlockCols * j + 32 * rb + 8 * k16,
+                          bdesc, kIdesc, (uint32_t)(((st - g.sb) | j | k16) != 0));
+            }
+          }
+          if (MC) tc_commit_mc(x_empty(s), (uint16_t)3);   // the stage is rewritten by BOTH CTAs' producers
+          else tc_commit(x_empty(s));     // the stage (smem tiles + TMEM blocks) is free once these MMAs have read it
+        }
+        tc_commit(acc_full);
+        u += g.se - g.sb;
       }
-      tc_commit(acc_full);
     }
   } else if (warp >= 4) {
-    // ================= dequant warps (then epilogue) =================
-    // set ws handles the ring stages ws, ws + kDequantSets, ... (all k-blocks of a stage); inside a set warp dw owns
-    // features 128 (dw / 4) + 32 (dw % 4) .. + 31 (its TMEM lane quadrant is warp % 4)
-    const int ws = (warp - 4) / (4 * NRB), dw = (warp - 4) % (4 * NRB), rb = dw >> 2, quad = dw & 3;
-    if (rb < nrb) {
-      const int f = n0 + 128 * rb + 32 * quad + lane;            // this lane's output feature
+    // ================= dequant warps (then epilogue), segment by segment =================
+    // set ws handles the segment's stages ws, ws + kDequantSets, ... (all k-blocks of a stage); inside a set warp dw owns
+    // features 32 dw .. 32 dw + 31 of the block (its TMEM lane quadrant is warp % 4)
+    const int ws = (warp - 4) / 4, quad = (warp - 4) % 4;
+    const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16);
+    int rit0 = 0, seg = 0;                          // ring iteration of the segment's first stage
+    for (int u = u_begin; u < u_end; ++seg) {
+      const GemmSeg g = seg_at(u);
+      const int tok0 = g.tok0, n0 = g.n0;
+      const int kb0 = g.sb * kKPS;                            // the segment's k-blocks [kb0, nkb)
+      const int nkb = min(p.nkb, g.se * kKPS);
+      const int f = n0 + 32 * quad + lane;                    // this lane's output feature
       const uint8_t* qrow = p.qw + (size_t)(f >> 2) * (size_t)(2 * p.K) + (size_t)((f & 3) * 32);
       const __half* owrow = p.ow ? p.ow + (size_t)f * p.r : nullptr;
-      const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16);
       // write one k-block (64 fp16 of this lane's feature) into its stage; the first block of a stage waits for
       // the stage to be free, the last one publishes the stage
       auto publish = [&](const uint32_t (&v)[32], int kb) {
-        const int st = (kb - kb0) / kKPS, j = (kb - kb0) - st * kKPS;      // (stage relative to this CTA's first)
-        const int as = st % kAStages, use = st / kAStages;
+        const int strel = (kb - kb0) / kKPS, j = (kb - kb0) - strel * kKPS;
+        const int rit = rit0 + strel;
+        const int as = rit % kAStages, use = rit / kAStages;
         if (j == 0 && use > 0) mbar_wait(a_empty(as), (uint32_t)((use - 1) & 1));
         tc_fence_after();
         tmem_st32(lane_taddr + (uint32_t)(kTmemA0 + Cfg::kAStageCols * as + Cfg::kABlockCols * j + 32 * rb), v);
@@ -236,7 +296,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
           if (lane == 0) mbar_arrive(a_full(as));
         }
       };
-      // this set's k-blocks: i-th = block (i % KPS) of stage ws + (i / KPS) * sets
+      // this set's k-blocks: i-th = block (i % KPS) of the segment's stage ws + (i / KPS) * sets
       auto kb_of = [&](int i) { return kb0 + (ws + (i / kKPS) * kDequantSets) * kKPS + (i % kKPS); };
       // Register prefetch ring over this set's k-blocks, kPF deep (weights come from L2, ~700 cycles away), scales
       // one group ahead.
@@ -247,7 +307,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       for (int i = 0; i < kPF; ++i) {
         ring[i][0] = ring[i][1] = make_uint4(0, 0, 0, 0);
         const int kb = kb_of(i);
-        if (kb < p.nkb_q) {
+        if (kb < nkb && kb < p.nkb_q) {
           ring[i][0] = ldg_nc_v4(qrow + (size_t)kb * 128);
           ring[i][1] = ldg_nc_v4(qrow + (size_t)kb * 128 + 16);
         }
@@ -260,22 +320,22 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
       const __half* zp = p.szeros + f;
       {
         const int kb = kb_of(0);
-        if (kb < p.nkb_q) { grp_next = kb / kb_per_grp; sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
+        if (kb < nkb && kb < p.nkb_q) { grp_next = kb / kb_per_grp; sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
       }
       bool done = false;
       for (int i0 = 0; !done; i0 += kPF) {
 #pragma unroll
-        for (int u = 0; u < kPF; ++u) {
-          const int i = i0 + u;
+        for (int uu = 0; uu < kPF; ++uu) {
+          const int i = i0 + uu;
           const int kb = kb_of(i);
           if (kb >= nkb) { done = true; break; }
           uint32_t v[32];
           if (kb < p.nkb_q) {
-            const uint4 c0 = ring[u][0], c1 = ring[u][1];
+            const uint4 c0 = ring[uu][0], c1 = ring[uu][1];
             const int kbn = kb_of(i + kPF);
-            if (kbn < p.nkb_q) {
-              ring[u][0] = ldg_nc_v4(qrow + (size_t)kbn * 128);
-              ring[u][1] = ldg_nc_v4(qrow + (size_t)kbn * 128 + 16);
+            if (kbn < nkb && kbn < p.nkb_q) {
+              ring[uu][0] = ldg_nc_v4(qrow + (size_t)kbn * 128);
+              ring[uu][1] = ldg_nc_v4(qrow + (size_t)kbn * 128 + 16);
             }
             const int g_now = kb / kb_per_grp;
             if (g_now != grp) {                        // entered a new group: take the prefetched pair (or load it)
@@ -293,7 +353,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
 #pragma unroll
               for (int a = 1; a <= 2 * kKPS; ++a) {
                 const int kba = kb_of(i + a);
-                if (grp_next < 0 && kba < p.nkb_q && kba / kb_per_grp != g_now) grp_next = kba / kb_per_grp;
+                if (grp_next < 0 && kba < nkb && kba < p.nkb_q && kba / kb_per_grp != g_now) grp_next = kba / kb_per_grp;
               }
               if (grp_next >= 0) { sn = ldg_nc_u16(sp + (size_t)grp_next * p.N); zn = ldg_nc_u16(zp + (size_t)grp_next * p.N); }
             }
@@ -329,17 +389,16 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
 
       // ---- epilogue: y^T tile (lane = feature, columns = tokens) -> + bias -> fp16 -> y[token, feature] ----
       // the sets split the token chunks of 32
-      mbar_wait(acc_full, 0);
+      mbar_wait(acc_full, (uint32_t)(seg & 1));
       tc_fence_after();
       const float bias = p.bias ? __half2float(p.bias[f]) : 0.f;
-      __half* stage = reinterpret_cast<__half*>(xs_gen + (warp - 4) * 2048);   // 32 tokens x 32 features per warp
-      const int fw = n0 + 128 * rb + 32 * quad;                                 // first feature of this warp
-      if (nsplit > 1) {
-        // ---- split-K: fp32 partial tile to the workspace; the CTA that arrives last adds all partials of the tile in
-        // split order (deterministic), adds the bias and stores fp16.  (semaphore reduce of gemm_cuda.cu:512-585, here
+      const int fw = n0 + 32 * quad;                                 // first feature of this warp
+      if (g.parts > 1) {
+        // ---- shared tile: fp32 partial to the workspace; the segment that arrives last adds all partials of the tile in
+        // part order (deterministic), adds the bias and stores fp16.  (semaphore reduce of gemm_cuda.cu:512-585, here
         // without the serialisation: only the last arrival reads.)
-        float* wsp = p.ws + (size_t)split * (size_t)p.M * (size_t)p.N;
-        float* stage_f = reinterpret_cast<float*>(xs_gen + (warp - 4) * 4096);   // 32 tokens x 32 features per warp
+        float* wsp = p.ws + (size_t)g.part * (size_t)p.M * (size_t)p.N;
+        float* stage_f = reinterpret_cast<float*>(stage_gen + (warp - 4) * 2048);   // 16 tokens x 32 features per warp
 #pragma unroll 1
         for (int tc = ws; tc < kBN / 32; tc += kDequantSets) {
           if (tok0 + 32 * tc >= p.M) break;
@@ -347,24 +406,27 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
           tmem_ld32(lane_taddr + (uint32_t)(kBN * rb + 32 * tc), acc);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 32; ++i) stage_f[i * 32 + lane] = __uint_as_float(acc[i]);
-          __syncwarp();
-          // 32 rows (tokens) of 128 bytes: 8 lanes per row, 4 rows per pass
+          for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-          for (int pass = 0; pass < 8; ++pass) {
-            const int row = pass * 4 + (lane >> 3), piece = lane & 7;
-            const int tok = tok0 + 32 * tc + row;
-            if (tok < p.M)
-              *reinterpret_cast<float4*>(wsp + (size_t)tok * (size_t)p.N + (size_t)(fw + piece * 4)) =
-                  *reinterpret_cast<const float4*>(stage_f + row * 32 + piece * 4);
+            for (int i = 0; i < 16; ++i) stage_f[i * 32 + lane] = __uint_as_float(acc[16 * hh + i]);
+            __syncwarp();
+            // 16 rows (tokens) of 128 bytes: 8 lanes per row, 4 rows per pass
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              const int row = pass * 4 + (lane >> 3), piece = lane & 7;
+              const int tok = tok0 + 32 * tc + 16 * hh + row;
+              if (tok < p.M)
+                *reinterpret_cast<float4*>(wsp + (size_t)tok * (size_t)p.N + (size_t)(fw + piece * 4)) =
+                    *reinterpret_cast<const float4*>(stage_f + row * 32 + piece * 4);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         tc_fence_before();
+        if (lane == 0) mbar_arrive(acc_empty);             // (this warp's reads of the accumulator are done)
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-        if (tid == 128) s_last = (atomicAdd(p.counters + tile, 1u) == (unsigned)(nsplit - 1)) ? 1u : 0u;
+        if (tid == 128) s_last = (atomicAdd(p.counters + g.tile, 1u) == (unsigned)(g.parts - 1)) ? 1u : 0u;
         asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
         if (s_last) {
           __threadfence();
@@ -373,7 +435,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
             const int tok = tok0 + (idx >> 5), c4 = idx & 31;
             const size_t off = (size_t)tok * (size_t)p.N + (size_t)(n0 + 4 * c4);
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < nsplit; ++z) {
+            for (int z = 0; z < g.parts; ++z) {
               const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + (size_t)z * (size_t)p.M * (size_t)p.N + off));
               a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
@@ -392,44 +454,49 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
             }
             *reinterpret_cast<uint2*>(p.y + (size_t)tok * (size_t)p.y_ld + (size_t)(n0 + 4 * c4)) = o;
           }
-          if (tid == 128) p.counters[tile] = 0u;          // ready for the next launch (stream order)
+          if (tid == 128) p.counters[g.tile] = 0u;          // ready for the next launch (stream order)
         }
-      } else
+      } else {
+        __half* stage = reinterpret_cast<__half*>(stage_gen + (warp - 4) * 2048);   // 32 tokens x 32 features per warp
 #pragma unroll 1
-      for (int tc = ws; tc < kBN / 32; tc += kDequantSets) {
-        uint32_t acc[32];
-        tmem_ld32(lane_taddr + (uint32_t)(kBN * rb + 32 * tc), acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int tc = ws; tc < kBN / 32; tc += kDequantSets) {
+          uint32_t acc[32];
+          tmem_ld32(lane_taddr + (uint32_t)(kBN * rb + 32 * tc), acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float val = __uint_as_float(acc[i]) + bias;
-          if (BF16) reinterpret_cast<__nv_bfloat16*>(stage)[i * 32 + lane] = __float2bfloat16_rn(val);
-          else stage[i * 32 + lane] = __float2half_rn(val);
-        }
-        __syncwarp();
-        // 32 rows (tokens) of 64 bytes: 4 lanes per row, 8 rows per pass
+          for (int i = 0; i < 32; ++i) {
+            const float val = __uint_as_float(acc[i]) + bias;
+            if (BF16) reinterpret_cast<__nv_bfloat16*>(stage)[i * 32 + lane] = __float2bfloat16_rn(val);
+            else stage[i * 32 + lane] = __float2half_rn(val);
+          }
+          __syncwarp();
+          // 32 rows (tokens) of 64 bytes: 4 lanes per row, 8 rows per pass
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          const int row = pass * 8 + (lane >> 2), piece = lane & 3;
-          const int tok = tok0 + 32 * tc + row;
-          const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + piece * 8);
-          if (tok < p.M) {
-            const size_t off = (size_t)tok * (size_t)p.y_ld + (size_t)(fw + piece * 8);
-            if (p.nranks == 0) {
-              *reinterpret_cast<uint4*>(p.y + off) = val;
-            } else if (p.y_mc) {
-              // one store to the multicast address: the switch replicates it to every rank (multimem.st lowers to
-              // this same STG.128 on the multicast mapping)
-              asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y_mc + off), "r"(val.x),
-                           "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-            } else {
-              for (int pr = 0; pr < p.nranks; ++pr) *reinterpret_cast<uint4*>(p.y_peer[pr] + off) = val;   // NVLink stores
+          for (int pass = 0; pass < 4; ++pass) {
+            const int row = pass * 8 + (lane >> 2), piece = lane & 3;
+            const int tok = tok0 + 32 * tc + row;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + piece * 8);
+            if (tok < p.M) {
+              const size_t off = (size_t)tok * (size_t)p.y_ld + (size_t)(fw + piece * 8);
+              if (p.nranks == 0) {
+                *reinterpret_cast<uint4*>(p.y + off) = val;
+              } else if (p.y_mc) {
+                // one store to the multicast address: the switch replicates it to every rank (multimem.st lowers to
+                // this same STG.128 on the multicast mapping)
+                asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y_mc + off), "r"(val.x),
+                             "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+              } else {
+                for (int pr = 0; pr < p.nranks; ++pr) *reinterpret_cast<uint4*>(p.y_peer[pr] + off) = val;   // NVLink stores
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(acc_empty);
       }
-      tc_fence_before();
+      rit0 += g.se - g.sb;
+      u += g.se - g.sb;
     }
   }
   __syncwarp();                      // the single-lane roles rejoin their warps
@@ -536,14 +603,15 @@ static int choose_splits(int tiles, int nst, int nsm) {
 }
 
 template <int NRB, int BN, bool MC, bool BF16>
-static int launch_gemm(const void* x, const GemmParams& prm_in, unsigned flags, cudaStream_t stream, bool allow_split = false) {
+static int launch_gemm(const void* x, const GemmParams& prm_in, unsigned flags, cudaStream_t stream, bool allow_split = false,
+                       bool allow_stream_k = false) {
   GemmParams prm = prm_in;
   using Cfg = GemmCfg<NRB, BN>;
   CUtensorMap xmap;
   int st = make_tmap_f16_2d(&xmap, x, (uint64_t)prm.M, (uint64_t)prm.K, MC ? BN / 2 : BN);
   if (st != QEFT_OK) return st;
   auto kern = gemm_w4_kernel<NRB, BN, MC, BF16>;
-  const size_t smem = (size_t)Cfg::kXStages * Cfg::kXStageBytes + 1024;
+  const size_t smem = (size_t)Cfg::kXStages * Cfg::kXStageBytes + (size_t)kDequantWarps * 2048 + 1024;   // ring + epilogue staging
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -567,6 +635,21 @@ static int launch_gemm(const void* x, const GemmParams& prm_in, unsigned flags, 
     }
   }
   cfg.gridDim = dim3((unsigned)cdiv(prm.M, BN), (unsigned)cdiv(prm.N, Cfg::kBM), (unsigned)splits);
+  if (allow_stream_k && splits == 1 && !MC) {
+    // stream-K: when the tiles do not fill whole waves (256 tiles on 148 SMs), one CTA per SM takes an equal contiguous
+    // share of the launch's (tile, stage) units; QEFT_GEMM_STREAMK=1 turns it on
+    static int nsm2 = 0;
+    if (nsm2 == 0 && (cudaDeviceGetAttribute(&nsm2, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm2 <= 0)) nsm2 = 148;
+    static const int sk_env = getenv("QEFT_GEMM_STREAMK") ? atoi(getenv("QEFT_GEMM_STREAMK")) : 0;   // (measured slower: DESIGN.md 3.2)
+    const int tiles = cdiv(prm.M, BN) * cdiv(prm.N, Cfg::kBM);
+    const int waves = cdiv(tiles, nsm2);
+    if (sk_env && tiles > nsm2 && tiles <= kSplitCounters && (long)waves * nsm2 * 100 > (long)tiles * 105) {
+      const int rc = split_workspace(stream, (size_t)2 * (size_t)prm.M * (size_t)prm.N * sizeof(float), &prm.ws, &prm.counters);
+      if (rc != QEFT_OK) return rc;
+      prm.stream_k = 1;
+      cfg.gridDim = dim3((unsigned)nsm2, 1, 1);
+    }
+  }
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -651,9 +734,9 @@ static int gemm_entry(const void* x, const void* qweight, const void* scales, co
   }
   // a few hundred tokens on a narrow layer still leave SMs idle (4096 x 11008 at M = 256: 32 tiles): K is split there too
   const bool split_ok = smallm_env && !gat && cdiv(M, 256) * (N / 128) <= 74;     // (at most half a wave of tiles)
-  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs, split_ok);
+  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs, split_ok, !gat);
   if (cfg_env == 3 && N % 256 == 0 && !gat) return launch_gemm<1, 256, true, false>(x, prm, flags, cs);
-  return launch_gemm<1, 256, false, false>(x, prm, flags, cs, split_ok);
+  return launch_gemm<1, 256, false, false>(x, prm, flags, cs, split_ok, !gat);
 }
 
 extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
