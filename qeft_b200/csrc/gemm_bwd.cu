@@ -94,21 +94,26 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(kDxBF, false, true) | (BF16 ? ((1u << 7) | (1u << 10)) : 0u);
+      // (this one thread issues every MMA of the CTA: its loop is kept free of descriptor arithmetic -- a descriptor's
+      // low field is the shared-memory address / 16, so a stage's descriptors are base + constant -- and of runtime trip
+      // counts)
+      const uint64_t adesc0 = make_sw128_desc(st0, 16, 1024), bdesc0 = make_sw128_desc(st0 + kDxABytes, kDxBK * 128, 1024);
+      const bool two = ntb == 2;
+      int s = 0;
+      uint32_t par = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kDxStages;
-        mbar_wait(full(s), (uint32_t)((kb / kDxStages) & 1));
+        mbar_wait(full(s), par);
         tc_fence_after();
-        const uint32_t a0 = st0 + s * kDxStageBytes, b0 = a0 + kDxABytes;
+        const uint64_t a = adesc0 + (uint64_t)((s * kDxStageBytes) >> 4), b = bdesc0 + (uint64_t)((s * kDxStageBytes) >> 4);
 #pragma unroll
         for (int k16 = 0; k16 < kDxBK / 16; ++k16) {
           // B: rows = n (k index of the MMA), 16 rows further per UMMA_K; 64-feature chunks 8 KB apart
-          const uint64_t bdesc = make_sw128_desc(b0 + k16 * 16 * 128, kDxBK * 128, 1024);
-          for (int tb = 0; tb < ntb; ++tb) {
-            const uint64_t adesc = make_sw128_desc(a0 + tb * (128 * kDxBK * 2) + k16 * 32, 16, 1024);
-            umma_ss_f16(tmem + 256 * tb, adesc, bdesc, idesc, (uint32_t)((kb | k16) != 0));
-          }
+          const uint32_t accf = (uint32_t)((kb | k16) != 0);
+          umma_ss_f16(tmem, a + (uint64_t)((k16 * 32) >> 4), b + (uint64_t)((k16 * 16 * 128) >> 4), idesc, accf);
+          if (two) umma_ss_f16(tmem + 256, a + (uint64_t)((128 * kDxBK * 2 + k16 * 32) >> 4), b + (uint64_t)((k16 * 16 * 128) >> 4), idesc, accf);
         }
         tc_commit(empty(s));
+        if (++s == kDxStages) { s = 0; par ^= 1u; }
       }
       tc_commit(acc_full);
     }

@@ -238,28 +238,35 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      int rit = 0, seg = 0;
+      // (this one thread issues every MMA of the CTA: no descriptor arithmetic -- a descriptor's low field is the shared-
+      // memory address / 16, so a stage's descriptors are base + constant --, no divisions, no runtime trip counts)
+      const uint64_t bdesc0 = make_b_desc(xs0);
+      int s = 0, seg = 0;
+      uint32_t par = 0;
       for (int u = u_begin; u < u_end; ++seg) {
         const GemmSeg g = seg_at(u);
         if (seg > 0) {                // the previous segment's accumulator has been read by all epilogue warps
           mbar_wait(acc_empty, (uint32_t)((seg - 1) & 1));
           tc_fence_after();
         }
-        for (int st = g.sb; st < g.se; ++st, ++rit) {
-          const int s = rit % kXStages;
-          mbar_wait(x_full(s), (uint32_t)((rit / kXStages) & 1));
+        for (int st = g.sb; st < g.se; ++st) {
+          mbar_wait(x_full(s), par);
           tc_fence_after();
-          const int nblk = min(kKPS, p.nkb - st * kKPS);
-          for (int j = 0; j < nblk; ++j) {
+          const uint64_t bs = bdesc0 + (uint64_t)((s * kXStageBytes) >> 4);
+          const uint32_t as = tmem + kTmemA0 + Cfg::kAStageCols * s;
+          const bool both = (st + 1) * kKPS <= p.nkb;          // (the tile's last stage may hold one k-block)
 #pragma unroll
-            for (int k16 = 0; k16 < kBK / 16; ++k16) {
-              const uint64_t bdesc = make_b_desc(xs0 + s * kXStageBytes + j * kXTileBytes + k16 * 32);
-              umma_ts_f16(tmem + kBN * rb, tmem + kTmemA0 + Cfg::kAStageCols * s + Cfg::kABlockCols * j + 32 * rb + 8 * k16,
-                          bdesc, kIdesc, (uint32_t)(((st - g.sb) | j | k16) != 0));
+          for (int j = 0; j < kKPS; ++j) {
+            if (j == 0 || both) {
+#pragma unroll
+              for (int k16 = 0; k16 < kBK / 16; ++k16)
+                umma_ts_f16(tmem, as + Cfg::kABlockCols * j + 8 * k16, bs + (uint64_t)((j * kXTileBytes + k16 * 32) >> 4), kIdesc,
+                            (uint32_t)(((st - g.sb) | j | k16) != 0));
             }
           }
           if (MC) tc_commit_mc(x_empty(s), (uint16_t)3);   // the stage is rewritten by BOTH CTAs' producers
           else tc_commit(x_empty(s));     // the stage (smem tiles + TMEM blocks) is free once these MMAs have read it
+          if (++s == kXStages) { s = 0; par ^= 1u; }
         }
         tc_commit(acc_full);
         u += g.se - g.sb;
