@@ -46,7 +46,7 @@ struct DxParams {
 
 template <bool BF16>
 __global__ void __launch_bounds__(kDxThreads, 1)
-gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
+gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap owmap, const DxParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kDxStages + 1];
   __shared__ uint32_t s_tmem_base;
@@ -62,8 +62,14 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
   const int nkb = p.N / kDxBK;
   const int ntb = (p.M - tok0) > 128 ? p.tbc : 1;   // token blocks with at least one live token
 
+  // The 16 dequant warps form two sets that alternate k-blocks; a thread converts TWO chunks (rows nl, nl + 32) of its
+  // set's k-blocks: per k-block the fixed latency of the hand-over (stage-free wait, proxy fence, arrival) is paid by one
+  // set while the other converts the next block.  The fp16 outlier columns K-r..K-1 are not converted at all: their
+  // rows of `oweight` ARE 128-byte rows of the MN-major swizzled tile, so the TMA producer drops them in place.
+  const int o_begin = p.ow != nullptr ? max(kf0, p.K - p.r) : p.K;        // outlier features of this tile: [o_begin, o_end)
+  const int o_end = min(kf0 + kDxBF, p.K);
   if (tid == 0) {
-    for (int s = 0; s < kDxStages; ++s) { mbar_init(full(s), 1 + kDxDequantWarps); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kDxStages; ++s) { mbar_init(full(s), 1 + kDxDequantWarps / 2); mbar_init(empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -85,9 +91,14 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kDxStages, use = kb / kDxStages;
         if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
-        mbar_expect_tx(full(s), (uint32_t)(ntb * 128 * kDxBK * 2));
+        const int nob = o_begin < o_end ? (o_end - o_begin) / 64 : 0;           // 64-feature boxes of oweight in this tile
+        mbar_expect_tx(full(s), (uint32_t)(ntb * 128 * kDxBK * 2 + nob * (kDxBK * 128)));
         for (int tb = 0; tb < ntb; ++tb)
           tma_load_2d(st0 + s * kDxStageBytes + tb * (128 * kDxBK * 2), &dymap, kb * kDxBK, tok0 + 128 * tb, full(s));
+        for (int ob = 0; ob < nob; ++ob) {
+          const int f = o_begin + 64 * ob;                                  // rows kb * 64 .. + 63 of oweight, columns f - (K - r) .. + 63
+          tma_load_2d(st0 + s * kDxStageBytes + kDxABytes + ((f - kf0) >> 6) * (kDxBK * 128), &owmap, f - (p.K - p.r), kb * kDxBK, full(s));
+        }
       }
     }
   } else if (warp == 1) {
@@ -120,81 +131,71 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const DxParams p) {
   } else if (warp >= 4) {
     // ================= dequant warps: one packed chunk (row n, 32 features) per thread and k-block =================
     const int dt = tid - 128;                 // 0..511
-    // row nl within the k-block, 32-feature chunk kc within the tile.  A quarter-warp (8 lanes = one wavefront of the
-    // 16-byte shared-memory stores below) is {both halves of a 64-feature chunk} x {the 4 rows of one qweight row}: its
-    // stores fall into 8 different 16-byte bank groups (the swizzle XORs the row into the chunk index) and its loads are
-    // one whole 128-byte packed tile.  (Round 1 put the 8 chunks of one row there: 4-way bank conflicts, 19 M per launch.)
-    const int kc = (dt & 1) | (((dt >> 3) & 3) << 1), nl = ((dt >> 1) & 3) | ((dt >> 5) << 2);
-    const int kf = kf0 + 32 * kc;             // first feature of this thread's chunk
-    const bool live = kf < p.K;
-    const bool outl = live && p.ow != nullptr && kf >= p.K - p.r;
-    const int grp = live ? kf / p.G : 0;
-    // packed byte offset inside a qweight row: 64-column tile, then (sub-row, half)
-    const size_t in_row = (size_t)(kf >> 6) * 128 + (size_t)(((kf >> 5) & 1) * 16);
-    // destination: 64-feature chunk kc/2 (8 KB apart), row nl, 16-byte chunks (kc%2)*4 + i, XOR-swizzled with nl%8
-    const uint32_t dst_row = (uint32_t)((kc >> 1) * (kDxBK * 128) + nl * 128);
-    const int sw = nl & 7;
-    // register prefetch ring, kPF k-blocks deep (weights and scales come from L2, ~700 cycles away)
-    constexpr int kPF = 4;
-    auto load_q = [&](int kb, uint4& q, uint32_t& sz) {
-      const int n = kb * kDxBK + nl;
-      q = ldg_nc_v4(p.qw + (size_t)(n >> 2) * (size_t)(2 * p.K) + (size_t)((n & 3) * 32) + in_row);
-      sz = (uint32_t)ldg_nc_u16(p.scales + (size_t)grp * p.N + n) | ((uint32_t)ldg_nc_u16(p.szeros + (size_t)grp * p.N + n) << 16);
-    };
-    auto load_o = [&](int kb, uint4 (&o)[4]) {
-      const __half* src = p.ow + (size_t)(kb * kDxBK + nl) * p.r + (kf - (p.K - p.r));
+    {
+      const int set = dt >> 8, d2 = dt & 255;
+      // (same quarter-warp composition as below: {both halves of a 64-feature chunk} x {the 4 rows of one qweight row})
+      const int kc = (d2 & 1) | (((d2 >> 3) & 3) << 1), nlb = ((d2 >> 1) & 3) | ((d2 >> 5) << 2);   // rows nlb, nlb + 32
+      const int kf = kf0 + 32 * kc;
+      const bool live = kf < p.K;
+      const bool outl = kf >= o_begin && kf < o_end;      // (the TMA producer fills these chunks)
+      const int grp = live ? kf / p.G : 0;
+      const size_t in_row = (size_t)(kf >> 6) * 128 + (size_t)(((kf >> 5) & 1) * 16);
+      const uint32_t dst_row = (uint32_t)((kc >> 1) * (kDxBK * 128) + nlb * 128);
+      const int sw = nlb & 7;
+      constexpr int kPF2 = 2;                 // the set's k-blocks in flight (= 4 k-blocks of the launch)
+      auto load_q = [&](int kb, int h, uint4& q, uint32_t& sz) {
+        const int n = kb * kDxBK + nlb + 32 * h;
+        q = ldg_nc_v4(p.qw + (size_t)(n >> 2) * (size_t)(2 * p.K) + (size_t)((n & 3) * 32) + in_row);
+        sz = (uint32_t)ldg_nc_u16(p.scales + (size_t)grp * p.N + n) | ((uint32_t)ldg_nc_u16(p.szeros + (size_t)grp * p.N + n) << 16);
+      };
+      uint4 ring[kPF2][2];
+      uint32_t rsz[kPF2][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = ldg_nc_v4(src + 8 * i);
-    };
-    uint4 ring[kPF];
-    uint32_t rsz[kPF];
-    uint4 onext[4];
+      for (int i = 0; i < kPF2; ++i)
 #pragma unroll
-    for (int i = 0; i < kPF; ++i) {
-      ring[i] = make_uint4(0, 0, 0, 0); rsz[i] = 0;
-      if (live && !outl && i < nkb) load_q(i, ring[i], rsz[i]);
-    }
+        for (int h = 0; h < 2; ++h) {
+          ring[i][h] = make_uint4(0, 0, 0, 0); rsz[i][h] = 0;
+          if (live && !outl && set + 2 * i < nkb) load_q(set + 2 * i, h, ring[i][h], rsz[i][h]);
+        }
+      bool done = false;
+      for (int i0 = 0; !done; i0 += kPF2) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) onext[i] = make_uint4(0, 0, 0, 0);
-    if (outl) load_o(0, onext);
-    for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
-#pragma unroll
-      for (int u = 0; u < kPF; ++u) {
-        const int kb = kb0 + u;
-        if (kb < nkb) {
+        for (int u = 0; u < kPF2; ++u) {
+          const int kb = set + 2 * (i0 + u);
+          if (kb >= nkb) { done = true; break; }
           const int s = kb % kDxStages, use = kb / kDxStages;
-          uint32_t v[16];
-          if (!live) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0u;
-          } else if (outl) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { v[4 * i + 0] = onext[i].x; v[4 * i + 1] = onext[i].y; v[4 * i + 2] = onext[i].z; v[4 * i + 3] = onext[i].w; }
-            if (kb + 1 < nkb) load_o(kb + 1, onext);
-          } else {
-            const uint4 q = ring[u];
-            const uint32_t sz = rsz[u];
-            if (kb + kPF < nkb) load_q(kb + kPF, ring[u], rsz[u]);
-            const uint32_t s2 = (sz & 0xffffu) | (sz << 16), z2 = (sz >> 16) | (sz & 0xffff0000u);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t hq[4];
-              unpack_word_to_half2(w[c], hq);                        // pairs k = 2 c + 8 j (+1), exact 0..15
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                v[c + 4 * j] = BF16 ? dequant_pair_bf16(hq[j], __half2float(__ushort_as_half((unsigned short)(sz & 0xffffu))),
-                                                        __half2float(__ushort_as_half((unsigned short)(sz >> 16))))
-                                    : hfma2_u32(hq[j], s2, z2);                        // w = fma(q, s, sz)
-            }
-          }
-          if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
           const uint32_t base = st0 + s * kDxStageBytes + kDxABytes + dst_row;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t a = base + (uint32_t)(((((kc & 1) << 2) + i) ^ sw) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]),
-                         "r"(v[4 * i + 3]) : "memory");
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[16];
+            if (!live) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0u;
+            } else if (!outl) {
+              const uint4 q = ring[u][h];
+              const uint32_t sz = rsz[u][h];
+              if (kb + 2 * kPF2 < nkb) load_q(kb + 2 * kPF2, h, ring[u][h], rsz[u][h]);
+              const uint32_t s2 = (sz & 0xffffu) | (sz << 16), z2 = (sz >> 16) | (sz & 0xffff0000u);
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t hq[4];
+                unpack_word_to_half2(w[c], hq);                        // pairs k = 2 c + 8 j (+1), exact 0..15
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  v[c + 4 * j] = BF16 ? dequant_pair_bf16(hq[j], __half2float(__ushort_as_half((unsigned short)(sz & 0xffffu))),
+                                                          __half2float(__ushort_as_half((unsigned short)(sz >> 16))))
+                                      : hfma2_u32(hq[j], s2, z2);                        // w = fma(q, s, sz)
+              }
+            }
+            if (h == 0 && use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
+            if (outl) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t a = base + (uint32_t)(h * 32 * 128) + (uint32_t)(((((kc & 1) << 2) + i) ^ sw) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]),
+                           "r"(v[4 * i + 3]) : "memory");
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -387,6 +388,11 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
   CUtensorMap dymap;
   int st = make_tmap_f16_2d(&dymap, dy, (uint64_t)M, (uint64_t)N, 128);
   if (st != QEFT_OK) return st;
+  // oweight [N, r] as 64 x 64 boxes: a box is the 64 rows of a k-block x 64 outlier features, i.e. 128-byte rows in the
+  // swizzled MN-major layout of the B tile (r == 0: a valid dummy map over dy, never used)
+  CUtensorMap owmap;
+  st = r > 0 ? make_tmap_f16_2d(&owmap, oweight, (uint64_t)N, (uint64_t)r, 64) : make_tmap_f16_2d(&owmap, dy, (uint64_t)M, (uint64_t)N, 64);
+  if (st != QEFT_OK) return st;
   DxParams prm;
   prm.qw = static_cast<const uint8_t*>(qweight);
   prm.scales = static_cast<const __half*>(scales);
@@ -418,8 +424,8 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (flags & QEFT_F_PDL) ? 1 : 0;
-  cudaError_t e = bf ? cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel<true>, dymap, prm)
-                     : cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel<false>, dymap, prm);
+  cudaError_t e = bf ? cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel<true>, dymap, owmap, prm)
+                     : cudaLaunchKernelEx(&cfg, gemm_w4_dx_kernel<false>, dymap, owmap, prm);
   if (e != cudaSuccess) return (int)e;
   count_launch();
   return QEFT_OK;
