@@ -142,7 +142,7 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
       const size_t in_row = (size_t)(kf >> 6) * 128 + (size_t)(((kf >> 5) & 1) * 16);
       const uint32_t dst_row = (uint32_t)((kc >> 1) * (kDxBK * 128) + nlb * 128);
       const int sw = nlb & 7;
-      constexpr int kPF2 = 2;                 // the set's k-blocks in flight (= 4 k-blocks of the launch)
+      constexpr int kPF2 = 3;                 // the set's k-blocks in flight (= 6 k-blocks of the launch)
       auto load_q = [&](int kb, int h, uint4& q, uint32_t& sz) {
         const int n = kb * kDxBK + nlb + 32 * h;
         q = ldg_nc_v4(p.qw + (size_t)(n >> 2) * (size_t)(2 * p.K) + (size_t)((n & 3) * 32) + in_row);
