@@ -740,7 +740,7 @@ def bench_gemm(model, M=2048, iters=10):
     _, tpeak, src = measured_peaks()
     h, f, _, kv = LLAMA_SHAPES[model]
     shapes = [("qkv/o_proj", h, h), ("gate/up_proj", f, h), ("down_proj", h, f)]
-    out = {"M": M, "tensor_peak_TFLOPs": tpeak, "peak_source": src, "dtype": "f16", "shapes": []}
+    out = {"M": M, "tensor_peak_TFLOPs": tpeak, "peak_source": src, "nominal_dense_f16_TFLOPs": 2250.0, "dtype": "f16", "shapes": []}
 
     def timeit(fn):
         for _ in range(3):
@@ -772,7 +772,9 @@ def bench_gemm(model, M=2048, iters=10):
         del xb, owb, yb
         out["shapes"].append({"name": name, "N": N, "K": K, "fwd_bf16_TFLOPs": flops / tfb / 1e12,
                               "fwd_TFLOPs": flops / tf / 1e12, "fwd_frac": flops / tf / 1e12 / tpeak,
+                              "fwd_frac_of_nominal_2250": flops / tf / 1e12 / 2250.0,
                               "dx_TFLOPs": flops / tb / 1e12, "dx_frac": flops / tb / 1e12 / tpeak,
+                              "dx_frac_of_nominal_2250": flops / tb / 1e12 / 2250.0,
                               "dow_us": tw * 1e6,
                               "finetune_step_TFLOPs": (2 * flops + 2.0 * M * N * 128) / (tf + tb + tw) / 1e12})
         del t, x, dy, y, dx
