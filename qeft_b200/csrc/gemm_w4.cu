@@ -89,7 +89,8 @@ struct GemmParams {
   // [split][M][N] and one arrival counter per tile; the CTA that arrives last adds the partials in split order
   float* ws;
   unsigned* counters;
-  int stream_k;            // one CTA per SM, each a contiguous range of the launch's (tile, stage) units
+  int stream_k;            // one CTA per SM: 1 = each a contiguous range of the launch's (tile, stage) units (stream-K),
+                           // 2 = each a contiguous range of whole tiles (persistent)
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row groups 1024
@@ -150,7 +151,13 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
   const int FB = p.N / 128;                                        // feature blocks
   // this CTA's range of (tile, stage) units [u_cur, u_end)
   int u_begin, u_end;            // (units fit 32 bits: at most 8192 tiles x a few hundred stages, times the grid)
-  if (p.stream_k) {
+  if (p.stream_k == 2) {
+    // persistent whole tiles: CTA c takes tiles [T c / G, T (c + 1) / G): TMEM allocation, barrier set-up and the
+    // tensor-map prefetch once per CTA, the TMA producer runs ahead into the next tile while this one is drained
+    const int T = cdiv(p.M, kBN) * FB;
+    u_begin = (int)(((long long)T * blockIdx.x) / gridDim.x) * nst_all;
+    u_end = (int)(((long long)T * (blockIdx.x + 1)) / gridDim.x) * nst_all;
+  } else if (p.stream_k) {
     const int U = cdiv(p.M, kBN) * FB * nst_all;
     u_begin = (int)(((long long)U * blockIdx.x) / gridDim.x);
     u_end = (int)(((long long)U * (blockIdx.x + 1)) / gridDim.x);
@@ -650,7 +657,11 @@ static int launch_gemm(const void* x, const GemmParams& prm_in, unsigned flags, 
     static const int sk_env = getenv("QEFT_GEMM_STREAMK") ? atoi(getenv("QEFT_GEMM_STREAMK")) : 0;   // (measured slower: DESIGN.md 3.2)
     const int tiles = cdiv(prm.M, BN) * cdiv(prm.N, Cfg::kBM);
     const int waves = cdiv(tiles, nsm2);
-    if (sk_env && tiles > nsm2 && tiles <= kSplitCounters && (long)waves * nsm2 * 100 > (long)tiles * 105) {
+    static const int persist_env = getenv("QEFT_GEMM_PERSIST") ? atoi(getenv("QEFT_GEMM_PERSIST")) : 1;   // (0: one CTA per tile)
+    if (persist_env && prm.nranks == 0 && tiles > nsm2) {     // (sharded launches: no gain measured, left one CTA per tile)
+      prm.stream_k = 2;
+      cfg.gridDim = dim3((unsigned)nsm2, 1, 1);
+    } else if (sk_env && prm.nranks == 0 && tiles > nsm2 && tiles <= kSplitCounters && (long)waves * nsm2 * 100 > (long)tiles * 105) {
       const int rc = split_workspace(stream, (size_t)2 * (size_t)prm.M * (size_t)prm.N * sizeof(float), &prm.ws, &prm.counters);
       if (rc != QEFT_OK) return rc;
       prm.stream_k = 1;
@@ -741,9 +752,9 @@ static int gemm_entry(const void* x, const void* qweight, const void* scales, co
   }
   // a few hundred tokens on a narrow layer still leave SMs idle (4096 x 11008 at M = 256: 32 tiles): K is split there too
   const bool split_ok = smallm_env && !gat && cdiv(M, 256) * (N / 128) <= 74;     // (at most half a wave of tiles)
-  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs, split_ok, !gat);
+  if (dtype == QEFT_DT_BF16) return launch_gemm<1, 256, false, true>(x, prm, flags, cs, split_ok, true);
   if (cfg_env == 3 && N % 256 == 0 && !gat) return launch_gemm<1, 256, true, false>(x, prm, flags, cs);
-  return launch_gemm<1, 256, false, false>(x, prm, flags, cs, split_ok, !gat);
+  return launch_gemm<1, 256, false, false>(x, prm, flags, cs, split_ok, true);
 }
 
 extern "C" int qeft_gemm_w4(const void* x, const void* qweight, const void* scales, const void* scaled_zeros,
