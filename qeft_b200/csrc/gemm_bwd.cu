@@ -19,6 +19,8 @@
 // (A = dy[tok, n0 .. n0+127], B = x_out[tok, 0 .. r-1]), fp32 accumulate, fp32 store / accumulate.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace qeft {
 
 // ======================================================================================================
@@ -33,6 +35,8 @@ constexpr int kDxBBytes = kDxBK * kDxBF * 2;           // dequantised weight til
 constexpr int kDxStageBytes = kDxABytes + kDxBBytes;
 constexpr int kDxDequantWarps = 16;
 constexpr int kDxThreads = (4 + kDxDequantWarps) * 32;
+constexpr int kDxMaxSplits = 4;           // contraction splits of a launch (gridDim.z)
+constexpr int kDxSplitCost = 23;          // fixed cost of a split CTA (partial round trip) in k-block times
 
 struct DxParams {
   const uint8_t* qw;
@@ -42,6 +46,11 @@ struct DxParams {
   __half* dx;              // [M, K]
   int M, N, K, r, G;
   int tbc;                 // 128-token blocks per CTA: 2, or 1 where that fills the SMs' waves better
+  // contraction split over gridDim.z (shapes whose tiles leave a nearly empty last wave, e.g. 13B K = 5120: 160 tiles on
+  // 148 SMs): fp32 partials [split][M][K] and one arrival counter per tile; the CTA of a tile that arrives last adds the
+  // partials in split order (deterministic) and stores dx; the counters reset themselves
+  float* ws;
+  unsigned* counters;
 };
 
 template <bool BF16>
@@ -50,6 +59,7 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kDxStages + 1];
   __shared__ uint32_t s_tmem_base;
+  __shared__ uint32_t s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t st0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_addr(bars);
@@ -59,7 +69,11 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
 
   const int tok0 = blockIdx.x * (128 * p.tbc);
   const int kf0 = blockIdx.y * kDxBF;
-  const int nkb = p.N / kDxBK;
+  // this CTA's k-blocks of the contraction: [kb_lo, kb_lo + nkb) (the whole of N unless the launch is split)
+  const int nkb_all = p.N / kDxBK;
+  const int nsplit = (int)gridDim.z;
+  const int kb_lo = (nkb_all * (int)blockIdx.z) / nsplit;
+  const int nkb = (nkb_all * ((int)blockIdx.z + 1)) / nsplit - kb_lo;
   const int ntb = (p.M - tok0) > 128 ? p.tbc : 1;   // token blocks with at least one live token
 
   // The 16 dequant warps form two sets that alternate k-blocks; a thread converts TWO chunks (rows nl, nl + 32) of its
@@ -88,8 +102,9 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&dymap) : "memory");
       pdl_wait();
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kDxStages, use = kb / kDxStages;
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb_lo + i;
+        const int s = i % kDxStages, use = i / kDxStages;
         if (use > 0) mbar_wait(empty(s), (uint32_t)((use - 1) & 1));
         const int nob = o_begin < o_end ? (o_end - o_begin) / 64 : 0;           // 64-feature boxes of oweight in this tile
         mbar_expect_tx(full(s), (uint32_t)(ntb * 128 * kDxBK * 2 + nob * (kDxBK * 128)));
@@ -155,13 +170,13 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           ring[i][h] = make_uint4(0, 0, 0, 0); rsz[i][h] = 0;
-          if (live && !outl && set + 2 * i < nkb) load_q(set + 2 * i, h, ring[i][h], rsz[i][h]);
+          if (live && !outl && set + 2 * i < nkb) load_q(kb_lo + set + 2 * i, h, ring[i][h], rsz[i][h]);
         }
       bool done = false;
       for (int i0 = 0; !done; i0 += kPF2) {
 #pragma unroll
         for (int u = 0; u < kPF2; ++u) {
-          const int kb = set + 2 * (i0 + u);
+          const int kb = set + 2 * (i0 + u);          // (relative to kb_lo)
           if (kb >= nkb) { done = true; break; }
           const int s = kb % kDxStages, use = kb / kDxStages;
           const uint32_t base = st0 + s * kDxStageBytes + kDxABytes + dst_row;
@@ -174,7 +189,7 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
             } else if (!outl) {
               const uint4 q = ring[u][h];
               const uint32_t sz = rsz[u][h];
-              if (kb + 2 * kPF2 < nkb) load_q(kb + 2 * kPF2, h, ring[u][h], rsz[u][h]);
+              if (kb + 2 * kPF2 < nkb) load_q(kb_lo + kb + 2 * kPF2, h, ring[u][h], rsz[u][h]);
               const uint32_t s2 = (sz & 0xffffu) | (sz << 16), z2 = (sz >> 16) | (sz & 0xffff0000u);
               const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -204,42 +219,127 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
       }
     }
 
-    // ---- epilogue: lanes = tokens, columns = features -> fp16, 16-byte stores ----
+    // ---- epilogue: TMEM lanes = tokens, columns = features.  A warp owns 32 tokens x 128 features; it passes 128-byte
+    // pieces of its rows through a private 4 KB staging tile (the ring is idle once acc_full has fired; 16-byte slots
+    // XOR-swizzled by the row, conflict-free both ways) so that a store instruction writes 4 whole 128-byte lines of
+    // dx (8 lanes per token row) instead of 16 bytes in each of 32 rows ----
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int dw = warp - 4, quad = dw & 3, tb = (dw >> 2) & 1, fh = dw >> 3;
-    const int tok = tok0 + 128 * tb + 32 * quad + lane;
     if (tb < ntb) {
       const uint32_t lane_taddr = tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(256 * tb + 128 * fh);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(lane_taddr + 32 * c, acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int f0 = kf0 + 128 * fh + 32 * c;
-        if (tok < p.M && f0 < p.K) {
-          __half* dst = p.dx + (size_t)tok * p.K + f0;
+      const uint32_t stg = st0 + (uint32_t)dw * 4096u;
+      const int trow0 = tok0 + 128 * tb + 32 * quad;           // first token of this warp
+      auto put = [&](int slot, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {     // this lane's row, 16-byte slot
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + (uint32_t)(lane * 128) + (uint32_t)(((slot ^ lane) & 7) << 4)),
+                     "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+      };
+      // 32 rows x 128 bytes of the staging tile -> global rows of `pitch` bytes starting at `dst`
+      auto flush = [&](uint8_t* dst, size_t pitch) {
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            auto pack2 = [](uint32_t a, uint32_t b) {
-              if (BF16) {
-                const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b));
-                return *reinterpret_cast<const uint32_t*>(&v);
-              }
-              const __half2 v = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
-              return *reinterpret_cast<const uint32_t*>(&v);
-            };
-            o.x = pack2(acc[8 * i + 0], acc[8 * i + 1]);
-            o.y = pack2(acc[8 * i + 2], acc[8 * i + 3]);
-            o.z = pack2(acc[8 * i + 4], acc[8 * i + 5]);
-            o.w = pack2(acc[8 * i + 6], acc[8 * i + 7]);
-            *reinterpret_cast<uint4*>(dst + 8 * i) = o;
+        for (int pass = 0; pass < 8; ++pass) {
+          const int row = pass * 4 + (lane >> 3), piece = lane & 7;
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(stg + (uint32_t)(row * 128) + (uint32_t)(((piece ^ row) & 7) << 4)) : "memory");
+          if (trow0 + row < p.M) *reinterpret_cast<uint4*>(dst + (size_t)row * pitch + (size_t)(piece * 16)) = v;
+        }
+        __syncwarp();
+      };
+      auto pack2 = [](uint32_t a, uint32_t b) {
+        if (BF16) {
+          const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b));
+          return *reinterpret_cast<const uint32_t*>(&v);
+        }
+        const __half2 v = __floats2half2_rn(__uint_as_float(a), __uint_as_float(b));
+        return *reinterpret_cast<const uint32_t*>(&v);
+      };
+      if (nsplit > 1) {
+        // fp32 partials: one 32-column chunk = 128 bytes per token
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(lane_taddr + 32 * c, acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int f0 = kf0 + 128 * fh + 32 * c;
+          if (f0 >= p.K) break;                                   // (warp-uniform; K % 64 == 0)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) put(j, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          flush(reinterpret_cast<uint8_t*>(p.ws + ((size_t)blockIdx.z * (size_t)p.M + (size_t)trow0) * (size_t)p.K + f0),
+                (size_t)p.K * sizeof(float));
+        }
+      } else {
+        // fp16 / bf16 result: two 32-column chunks = 128 bytes per token
+#pragma unroll 1
+        for (int cp = 0; cp < 2; ++cp) {
+          const int f0 = kf0 + 128 * fh + 64 * cp;
+          if (f0 >= p.K) break;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t acc[32];
+            tmem_ld32(lane_taddr + 64 * cp + 32 * h, acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              put(4 * h + i, pack2(acc[8 * i + 0], acc[8 * i + 1]), pack2(acc[8 * i + 2], acc[8 * i + 3]),
+                  pack2(acc[8 * i + 4], acc[8 * i + 5]), pack2(acc[8 * i + 6], acc[8 * i + 7]));
           }
+          flush(reinterpret_cast<uint8_t*>(p.dx + (size_t)trow0 * (size_t)p.K + f0), (size_t)p.K * sizeof(__half));
         }
       }
     }
     tc_fence_before();
+    if (nsplit > 1) {
+      // the split that arrives last at its tile adds the partials (split order) and stores the tile
+      const int tile = (int)(blockIdx.x * gridDim.y + blockIdx.y);
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(kDxDequantWarps * 32) : "memory");
+      if (tid == 128) s_last = (atomicAdd(p.counters + tile, 1u) == (unsigned)(nsplit - 1)) ? 1u : 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(kDxDequantWarps * 32) : "memory");
+      if (s_last) {
+        __threadfence();
+        const int ntok = min(128 * p.tbc, p.M - tok0), nf4 = min(kDxBF, p.K - kf0) / 4;
+        const size_t part = (size_t)p.M * (size_t)p.K;
+        // (one SM reads nsplit x 256 KB from L2: 4 positions x up to 4 splits of loads in flight per thread)
+        constexpr int kU = 4, kStride = kDxDequantWarps * 32;
+        const int total = ntok * (kDxBF / 4);
+#pragma unroll 1
+        for (int base = tid - 128; base < total; base += kU * kStride) {
+          size_t off[kU];
+          bool ok[kU];
+          float4 v[kU][kDxMaxSplits];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int idx = base + u * kStride;
+            const int t = idx / (kDxBF / 4), c4 = idx % (kDxBF / 4);
+            ok[u] = idx < total && c4 < nf4;
+            off[u] = (size_t)(tok0 + t) * (size_t)p.K + (size_t)(kf0 + 4 * c4);
+#pragma unroll
+            for (int z = 0; z < kDxMaxSplits; ++z)
+              if (ok[u] && z < nsplit) v[u][z] = __ldcg(reinterpret_cast<const float4*>(p.ws + (size_t)z * part + off[u]));
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            if (!ok[u]) continue;
+            float4 a = v[u][0];
+#pragma unroll
+            for (int z = 1; z < kDxMaxSplits; ++z)
+              if (z < nsplit) { a.x += v[u][z].x; a.y += v[u][z].y; a.z += v[u][z].z; a.w += v[u][z].w; }
+            uint2 o;
+            if (BF16) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+              o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            } else {
+              const __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
+              o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            }
+            *reinterpret_cast<uint2*>(p.dx + off[u]) = o;
+          }
+        }
+        if (tid == 128) p.counters[tile] = 0u;          // ready for the next launch (stream order)
+      }
+    }
   }
   __syncwarp();
   __syncthreads();
@@ -409,13 +509,42 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
     static const int tbc_env = getenv("QEFT_DX_TBC") ? atoi(getenv("QEFT_DX_TBC")) : 0;
     prm.tbc = tbc_env == 1 ? 1 : 2;
   }
+  // Contraction split (gridDim.z): cost of a launch in k-block times = waves of CTAs x (k-blocks per split + the fixed
+  // cost of a CTA); a split must win by 3 %.
+  int splits = 1;
+  prm.ws = nullptr; prm.counters = nullptr;
+  {
+    static const int split_env = getenv("QEFT_DX_SPLITS") ? atoi(getenv("QEFT_DX_SPLITS")) : 0;      // 1: never split
+    int dev = 0, nsm = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+    const int tiles = cdiv(M, 128 * prm.tbc) * cdiv(K, kDxBF), nkb = N / kDxBK;
+    if (split_env > 1) {
+      splits = split_env < nkb / 4 ? split_env : (nkb / 4 > 0 ? nkb / 4 : 1);
+      if (splits > kDxMaxSplits) splits = kDxMaxSplits;
+    } else if (split_env == 0) {
+      // (measured on B200: a k-block 0.75 us, an unsplit CTA ~1.5 us on top = 2 k-blocks, a split CTA 17 us = 23 --
+      // the fp32 partial round trip.  13B 13824 x 5120, M = 2048: 160 tiles = 2 waves, 324 us unsplit, 291 / 283 at 2 / 3
+      // splits; 5120 x 5120: 118 us unsplit, 144 / 154: not split.  Launches of a few tiles, M <= 512: 1.4-2.5 x faster.)
+      long best = (long)cdiv(tiles, nsm) * (nkb + 2) * 100;
+      for (int sp = 2; sp <= kDxMaxSplits && nkb / sp >= 12; ++sp) {
+        const long cost = (long)cdiv(tiles * sp, nsm) * (cdiv(nkb, sp) + kDxSplitCost) * 103;
+        if (cost < best) { best = cost * 100 / 103; splits = sp; }
+      }
+    }
+    if (tiles > kSplitCounters || (size_t)splits * (size_t)M * (size_t)K * sizeof(float) > ((size_t)1 << 30)) splits = 1;
+    if (splits > 1) {
+      st = split_workspace(static_cast<cudaStream_t>(stream), (size_t)splits * (size_t)M * (size_t)K * sizeof(float), &prm.ws, &prm.counters);
+      if (st != QEFT_OK) return st;
+    }
+  }
   const size_t smem = (size_t)kDxStages * kDxStageBytes + 1024;
   static bool done[2][64] = {};
   const bool bf = dtype == QEFT_DT_BF16;
   st = bf ? set_smem_once(gemm_w4_dx_kernel<true>, smem, done[1]) : set_smem_once(gemm_w4_dx_kernel<false>, smem, done[0]);
   if (st != QEFT_OK) return st;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cdiv(M, 128 * prm.tbc), (unsigned)cdiv(K, kDxBF));
+  cfg.gridDim = dim3((unsigned)cdiv(M, 128 * prm.tbc), (unsigned)cdiv(K, kDxBF), (unsigned)splits);
   cfg.blockDim = dim3(kDxThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);

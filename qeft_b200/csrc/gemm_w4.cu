@@ -445,28 +445,52 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
         if (s_last) {
           __threadfence();
           const int ntok = min(kBN, p.M - tok0);
-          for (int idx = tid - 128; idx < ntok * 32; idx += kDequantWarps * 32) {
-            const int tok = tok0 + (idx >> 5), c4 = idx & 31;
-            const size_t off = (size_t)tok * (size_t)p.N + (size_t)(n0 + 4 * c4);
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < g.parts; ++z) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + (size_t)z * (size_t)p.M * (size_t)p.N + off));
-              a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          // (one SM reads parts x 128 KB from L2: 8 positions of loads in flight per thread)
+          constexpr int kU = 8, kStride = kDequantWarps * 32;
+          const int total = ntok * 32;
+          const size_t partsz = (size_t)p.M * (size_t)p.N;
+#pragma unroll 1
+          for (int base = tid - 128; base < total; base += kU * kStride) {
+            size_t off[kU];
+            float4 a[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int idx = base + u * kStride;
+              off[u] = (size_t)(tok0 + (idx >> 5)) * (size_t)p.N + (size_t)(n0 + 4 * (idx & 31));
+              a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (idx < total) a[u] = __ldcg(reinterpret_cast<const float4*>(p.ws + off[u]));
             }
-            if (p.bias) {
-              const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + n0 + 4 * c4);
-              const float2 b01 = half2_bits_to_float2(bb.x), b23 = half2_bits_to_float2(bb.y);
-              a.x += b01.x; a.y += b01.y; a.z += b23.x; a.w += b23.y;
+            for (int z = 1; z < g.parts; ++z) {
+              float4 v[kU];
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + u * kStride < total) v[u] = __ldcg(reinterpret_cast<const float4*>(p.ws + (size_t)z * partsz + off[u]));
+              }
+#pragma unroll
+              for (int u = 0; u < kU; ++u) { a[u].x += v[u].x; a[u].y += v[u].y; a[u].z += v[u].z; a[u].w += v[u].w; }
             }
-            uint2 o;
-            if (BF16) {
-              const __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-              o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
-            } else {
-              const __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
-              o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int idx = base + u * kStride;
+              if (idx >= total) continue;
+              const int c4 = idx & 31;
+              float4 r4 = a[u];
+              if (p.bias) {
+                const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + n0 + 4 * c4);
+                const float2 b01 = half2_bits_to_float2(bb.x), b23 = half2_bits_to_float2(bb.y);
+                r4.x += b01.x; r4.y += b01.y; r4.z += b23.x; r4.w += b23.y;
+              }
+              uint2 o;
+              if (BF16) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(r4.x, r4.y), hi = __floats2bfloat162_rn(r4.z, r4.w);
+                o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+              } else {
+                const __half2 lo = __floats2half2_rn(r4.x, r4.y), hi = __floats2half2_rn(r4.z, r4.w);
+                o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+              }
+              *reinterpret_cast<uint2*>(p.y + (size_t)(tok0 + (idx >> 5)) * (size_t)p.y_ld + (size_t)(n0 + 4 * c4)) = o;
             }
-            *reinterpret_cast<uint2*>(p.y + (size_t)tok * (size_t)p.y_ld + (size_t)(n0 + 4 * c4)) = o;
           }
           if (tid == 128) p.counters[g.tile] = 0u;          // ready for the next launch (stream order)
         }
@@ -574,8 +598,7 @@ int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 // different streams never share it; grown on demand.  The first split-K launch on a stream allocates (cudaMalloc), so
 // it must happen before that stream is captured into a CUDA graph (a warm-up call, as torch requires anyway).
 struct SplitWs { int dev; cudaStream_t stream; float* ws; size_t bytes; unsigned* counters; };
-constexpr int kSplitCounters = 8192;
-static int split_workspace(cudaStream_t stream, size_t bytes, float** ws, unsigned** counters) {
+int split_workspace(cudaStream_t stream, size_t bytes, float** ws, unsigned** counters) {
   static std::vector<SplitWs> pool;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);

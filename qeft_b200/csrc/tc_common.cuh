@@ -117,5 +117,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n, bool a_mn_major, bo
 // 2-D TMA map of a row-major fp16 matrix [rows, cols]: box = 64 columns (128 bytes, swizzled) x box_rows rows
 int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int make_tmap_f16_2d_pitched(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows);
+// fp32 partial-tile workspace + self-resetting per-tile arrival counters of the split launches (forward split-K, dX
+// contraction split), one set per (device, stream); defined in gemm_w4.cu
+constexpr int kSplitCounters = 8192;
+int split_workspace(cudaStream_t stream, size_t bytes, float** ws, unsigned** counters);
 
 }  // namespace qeft

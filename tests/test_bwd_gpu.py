@@ -26,6 +26,9 @@ def dev(a):
     (200, 384, 320, 64, 64),        # ragged tokens, K % 256 != 0 (feature tile is clipped), G = 64
     (300, 128, 1024, 192, 256),     # three token blocks, r = 192
     (512, 1024, 768, 128, 768),     # per-channel scales
+    (256, 2048, 512, 128, 128),     # few tiles, long contraction: split over N (2 splits), fp32 partials + last-arriver sum
+    (300, 3072, 320, 64, 64),       # 4 splits, ragged tokens and a clipped feature tile in the partial round trip
+    (640, 4096, 1024, 128, 128),    # 3 token tiles x 4 feature tiles x 4 splits
 ])
 def test_dx_matches_oracle(M, N, K, r, G):
     from qeft_b200 import qeft_cuda
@@ -39,6 +42,12 @@ def test_dx_matches_oracle(M, N, K, r, G):
     torch.cuda.synchronize()
     assert got.shape == (M, K) and got.dtype == torch.float16
     assert rel_err(got.cpu().numpy(), want_dx) <= REL_TOL, rel_err(got.cpu().numpy(), want_dx)
+    # a second launch gives the same bits (split launches: the arrival counters reset themselves, the partials are
+    # added in split order)
+    again = qeft_cuda.gemm_w4_dx(dev(dy), dev(L["qweight"]), dev(L["scales"]), dev(L["scaled_zeros"]),
+                                 dev(L["oweight"]) if r > 0 else None, K, group_size=G, pdl=False)
+    torch.cuda.synchronize()
+    assert torch.equal(got, again)
 
 
 @pytest.mark.parametrize("M,N,K,r", [(64, 128, 256, 64), (300, 256, 512, 128), (1000, 384, 384, 256)])
