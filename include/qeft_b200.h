@@ -224,6 +224,11 @@ QEFT_API int qeft_gemm_w4_gather(const void* x, const void* qweight, const void*
  * Backward wrt the input:  dx[M, K] = dy[M, N] . Wdense   (same packed bytes, contraction over N).
  * The math BASELINE.json defines for QuantMatMulQEFT.backward (the reference's qlinear.py:28-44 is
  * not usable).
+ * Launches that would leave SMs idle (few tiles, or a nearly empty last wave) are split along the contraction: fp32
+ * partial tiles go through a workspace owned by the (device, stream) pair -- the same one as qeft_gemm_w4's split-K --
+ * and the last CTA to arrive at a tile adds them in split order (results do not depend on scheduling; two launches are
+ * bit-equal).  The first split launch on a stream allocates the workspace (cudaMalloc): run one before capturing that
+ * stream into a CUDA graph.
  */
 QEFT_API int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* scales, const void* scaled_zeros,
                     const void* oweight, void* dx, int M, int N, int K, int r, int G,
