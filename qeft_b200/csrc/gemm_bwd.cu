@@ -35,7 +35,7 @@ constexpr int kDxBBytes = kDxBK * kDxBF * 2;           // dequantised weight til
 constexpr int kDxStageBytes = kDxABytes + kDxBBytes;
 constexpr int kDxDequantWarps = 16;
 constexpr int kDxThreads = (4 + kDxDequantWarps) * 32;
-constexpr int kDxMaxSplits = 4;           // contraction splits of a launch (gridDim.z)
+constexpr int kDxMaxSplits = 4;           // CTAs that may share a tile (contraction split)
 constexpr int kDxSplitCost = 23;          // fixed cost of a split CTA (partial round trip) in k-block times
 
 struct DxParams {
@@ -46,9 +46,13 @@ struct DxParams {
   __half* dx;              // [M, K]
   int M, N, K, r, G;
   int tbc;                 // 128-token blocks per CTA: 2, or 1 where that fills the SMs' waves better
-  // contraction split over gridDim.z (shapes whose tiles leave a nearly empty last wave, e.g. 13B K = 5120: 160 tiles on
-  // 148 SMs): fp32 partials [split][M][K] and one arrival counter per tile; the CTA of a tile that arrives last adds the
-  // partials in split order (deterministic) and stores dx; the counters reset themselves
+  // The grid is a 1-D list of CTAs over the tiles (token tile fastest): the first t_main CTAs compute whole tiles, the
+  // others come in groups of `splits` that share one of the remaining tiles, each over a contiguous range of the
+  // contraction (launches of few tiles: t_main = 0; launches whose last wave is nearly empty, e.g. 13B K = 5120 with 160
+  // tiles on 148 SMs: only the tiles of that wave).  fp32 partials [split][M][K] and one arrival counter per tile; the
+  // CTA of a tile that arrives last adds the partials in split order (deterministic) and stores dx; the counters reset
+  // themselves.
+  int ttok, t_main, splits;
   float* ws;
   unsigned* counters;
 };
@@ -67,13 +71,19 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
   auto empty = [&](int s) { return bar0 + 8 * (kDxStages + s); };
   const uint32_t acc_full = bar0 + 8 * (2 * kDxStages);
 
-  const int tok0 = blockIdx.x * (128 * p.tbc);
-  const int kf0 = blockIdx.y * kDxBF;
+  int tile = (int)blockIdx.x, zsp = 0, nsplit = 1;
+  if (tile >= p.t_main) {
+    const int q = tile - p.t_main;
+    tile = p.t_main + q / p.splits;
+    zsp = q - (q / p.splits) * p.splits;
+    nsplit = p.splits;
+  }
+  const int tok0 = (tile % p.ttok) * (128 * p.tbc);
+  const int kf0 = (tile / p.ttok) * kDxBF;
   // this CTA's k-blocks of the contraction: [kb_lo, kb_lo + nkb) (the whole of N unless the launch is split)
   const int nkb_all = p.N / kDxBK;
-  const int nsplit = (int)gridDim.z;
-  const int kb_lo = (nkb_all * (int)blockIdx.z) / nsplit;
-  const int nkb = (nkb_all * ((int)blockIdx.z + 1)) / nsplit - kb_lo;
+  const int kb_lo = (nkb_all * zsp) / nsplit;
+  const int nkb = (nkb_all * (zsp + 1)) / nsplit - kb_lo;
   const int ntb = (p.M - tok0) > 128 ? p.tbc : 1;   // token blocks with at least one live token
 
   // The 16 dequant warps form two sets that alternate k-blocks; a thread converts TWO chunks (rows nl, nl + 32) of its
@@ -266,7 +276,7 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
           if (f0 >= p.K) break;                                   // (warp-uniform; K % 64 == 0)
 #pragma unroll
           for (int j = 0; j < 8; ++j) put(j, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          flush(reinterpret_cast<uint8_t*>(p.ws + ((size_t)blockIdx.z * (size_t)p.M + (size_t)trow0) * (size_t)p.K + f0),
+          flush(reinterpret_cast<uint8_t*>(p.ws + ((size_t)zsp * (size_t)p.M + (size_t)trow0) * (size_t)p.K + f0),
                 (size_t)p.K * sizeof(float));
         }
       } else {
@@ -292,7 +302,6 @@ gemm_w4_dx_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
     tc_fence_before();
     if (nsplit > 1) {
       // the split that arrives last at its tile adds the partials (split order) and stores the tile
-      const int tile = (int)(blockIdx.x * gridDim.y + blockIdx.y);
       __threadfence();
       asm volatile("bar.sync 1, %0;" ::"n"(kDxDequantWarps * 32) : "memory");
       if (tid == 128) s_last = (atomicAdd(p.counters + tile, 1u) == (unsigned)(nsplit - 1)) ? 1u : 0u;
@@ -509,42 +518,52 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
     static const int tbc_env = getenv("QEFT_DX_TBC") ? atoi(getenv("QEFT_DX_TBC")) : 0;
     prm.tbc = tbc_env == 1 ? 1 : 2;
   }
-  // Contraction split (gridDim.z): cost of a launch in k-block times = waves of CTAs x (k-blocks per split + the fixed
-  // cost of a CTA); a split must win by 3 %.
-  int splits = 1;
+  // Contraction split: cost of a launch in k-block times = sum over its waves of (k-blocks per CTA + the fixed cost of a
+  // CTA); a split must win by 3 %.  Measured on B200: a k-block 0.75 us, an unsplit CTA ~1.5 us on top = 2 k-blocks, a
+  // split CTA 17 us = 23 (the fp32 partial round trip).  Splitting every tile pays for launches of few tiles (M <= 512:
+  // 1.4-2.5 x faster); at M = 2048 only the tiles of a nearly empty last wave are split (13B K = 5120: 160 tiles; 7B
+  // K = 11008: 344).  QEFT_DX_SPLITS=1: never, =n: every tile n ways; QEFT_DX_TAIL=n: the last wave n ways.
+  const int ttok = cdiv(M, 128 * prm.tbc), tiles = ttok * cdiv(K, kDxBF);
+  int splits = 1, t_main = tiles;
   prm.ws = nullptr; prm.counters = nullptr;
   {
-    static const int split_env = getenv("QEFT_DX_SPLITS") ? atoi(getenv("QEFT_DX_SPLITS")) : 0;      // 1: never split
+    static const int split_env = getenv("QEFT_DX_SPLITS") ? atoi(getenv("QEFT_DX_SPLITS")) : 0;
+    static const int tail_env = getenv("QEFT_DX_TAIL") ? atoi(getenv("QEFT_DX_TAIL")) : 0;
     int dev = 0, nsm = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
-    const int tiles = cdiv(M, 128 * prm.tbc) * cdiv(K, kDxBF), nkb = N / kDxBK;
-    if (split_env > 1) {
-      splits = split_env < nkb / 4 ? split_env : (nkb / 4 > 0 ? nkb / 4 : 1);
-      if (splits > kDxMaxSplits) splits = kDxMaxSplits;
+    const int nkb = N / kDxBK;
+    const int sp_max = nkb / 12 < kDxMaxSplits ? nkb / 12 : kDxMaxSplits;     // (a split keeps at least 12 k-blocks)
+    if (tail_env > 1) {
+      if (tiles > nsm && tiles % nsm != 0 && sp_max >= 2) { splits = tail_env < sp_max ? tail_env : sp_max; t_main = tiles - tiles % nsm; }
+    } else if (split_env > 1) {
+      if (sp_max >= 2) { splits = split_env < sp_max ? split_env : sp_max; t_main = 0; }
     } else if (split_env == 0) {
-      // (measured on B200: a k-block 0.75 us, an unsplit CTA ~1.5 us on top = 2 k-blocks, a split CTA 17 us = 23 --
-      // the fp32 partial round trip.  13B 13824 x 5120, M = 2048: 160 tiles = 2 waves, 324 us unsplit, 291 / 283 at 2 / 3
-      // splits; 5120 x 5120: 118 us unsplit, 144 / 154: not split.  Launches of a few tiles, M <= 512: 1.4-2.5 x faster.)
       long best = (long)cdiv(tiles, nsm) * (nkb + 2) * 100;
-      for (int sp = 2; sp <= kDxMaxSplits && nkb / sp >= 12; ++sp) {
-        const long cost = (long)cdiv(tiles * sp, nsm) * (cdiv(nkb, sp) + kDxSplitCost) * 103;
-        if (cost < best) { best = cost * 100 / 103; splits = sp; }
+      for (int sp = 2; sp <= sp_max; ++sp) {
+        const long part = cdiv(nkb, sp) + kDxSplitCost;
+        const long all = (long)cdiv(tiles * sp, nsm) * part * 103;
+        if (all < best) { best = all * 100 / 103; splits = sp; t_main = 0; }
+        if (tiles > nsm && tiles % nsm != 0) {
+          const long tail = ((long)(tiles / nsm) * (nkb + 2) + (long)cdiv((tiles % nsm) * sp, nsm) * part) * 103;
+          if (tail < best) { best = tail * 100 / 103; splits = sp; t_main = tiles - tiles % nsm; }
+        }
       }
     }
-    if (tiles > kSplitCounters || (size_t)splits * (size_t)M * (size_t)K * sizeof(float) > ((size_t)1 << 30)) splits = 1;
+    if (tiles > kSplitCounters || (size_t)splits * (size_t)M * (size_t)K * sizeof(float) > ((size_t)1 << 30)) { splits = 1; t_main = tiles; }
     if (splits > 1) {
       st = split_workspace(static_cast<cudaStream_t>(stream), (size_t)splits * (size_t)M * (size_t)K * sizeof(float), &prm.ws, &prm.counters);
       if (st != QEFT_OK) return st;
     }
   }
+  prm.ttok = ttok; prm.t_main = t_main; prm.splits = splits;
   const size_t smem = (size_t)kDxStages * kDxStageBytes + 1024;
   static bool done[2][64] = {};
   const bool bf = dtype == QEFT_DT_BF16;
   st = bf ? set_smem_once(gemm_w4_dx_kernel<true>, smem, done[1]) : set_smem_once(gemm_w4_dx_kernel<false>, smem, done[0]);
   if (st != QEFT_OK) return st;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cdiv(M, 128 * prm.tbc), (unsigned)cdiv(K, kDxBF), (unsigned)splits);
+  cfg.gridDim = dim3((unsigned)(t_main + (tiles - t_main) * splits));
   cfg.blockDim = dim3(kDxThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
