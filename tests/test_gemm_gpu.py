@@ -16,6 +16,17 @@ def rel_err(got, want):
     return float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-6))
 
 
+def assert_close(got, want, what="", atol_rms=2e-3):
+    """Elementwise form of the tolerance (beside the global-normalised rel_err): |err| <= 1e-3 |ref| + 2e-3 rms(ref).
+    rtol covers a one-ulp flip of the fp16 result (2^-10); the rms term covers what does not scale with |y| (fp16
+    rounding of the weights' fma, summation order), so small-magnitude outputs are checked too."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    rms = float(np.sqrt(np.mean(want ** 2))) + 1e-12
+    bad = np.abs(got - want) > 1e-3 * np.abs(want) + atol_rms * rms
+    assert not bad.any(), (what, int(bad.sum()), float(np.max(np.abs(got - want)) / rms))
+
+
 def dev(a):
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()
 
@@ -44,6 +55,7 @@ def test_gemm_matches_oracle(M, N, K, r, G):
     got = run_gemm(L, x, bias=L["bias"])
     assert got.shape == (M, N) and got.dtype == np.float16
     assert rel_err(got, want) <= REL_TOL, rel_err(got, want)
+    assert_close(got, want)
 
 
 @pytest.mark.parametrize("M,N,K,r,G", [
@@ -65,6 +77,7 @@ def test_small_m_split_k_matches_oracle(M, N, K, r, G):
     got = run_gemm(L, x, bias=L["bias"])
     assert got.shape == (M, N) and got.dtype == np.float16
     assert rel_err(got, want) <= REL_TOL, rel_err(got, want)
+    assert_close(got, want)
     again = run_gemm(L, x, bias=L["bias"])
     assert np.array_equal(got.view(np.int16), again.view(np.int16))
 

@@ -16,6 +16,17 @@ def rel_err(got, want):
     return float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-6))
 
 
+def assert_close(got, want, what="", atol_rms=2e-3):
+    """Elementwise form of the tolerance (beside the global-normalised rel_err): |err| <= 1e-3 |ref| + 2e-3 rms(ref).
+    rtol covers a one-ulp flip of the fp16 result (2^-10); the rms term covers what does not scale with |y| (fp16
+    rounding of the weights' fma, summation order), so small-magnitude outputs are checked too."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    rms = float(np.sqrt(np.mean(want ** 2))) + 1e-12
+    bad = np.abs(got - want) > 1e-3 * np.abs(want) + atol_rms * rms
+    assert not bad.any(), (what, int(bad.sum()), float(np.max(np.abs(got - want)) / rms))
+
+
 def dev(a):
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()
 
@@ -50,6 +61,7 @@ def test_gemv_matches_oracle(N, K, r, G, m):
         got = run_gemv(L, x, layout, bias=L["bias"])
         assert got.shape == (m, N) and got.dtype == np.float16
         assert rel_err(got, want) <= REL_TOL, (layout, rel_err(got, want))
+        assert_close(got, want)
 
 
 @pytest.mark.parametrize("shape", [(11008, 4096), (4096, 11008)])
@@ -77,6 +89,7 @@ def test_gemv_uncommon_shapes(N, K, r, m):
     for layout in (_lib.OW_INTERLEAVED, _lib.OW_PLAIN):
         got = run_gemv(L, x, layout, bias=L["bias"])
         assert rel_err(got, want) <= REL_TOL, (layout, rel_err(got, want))
+        assert_close(got, want)
 
 
 def test_gemv_o_proj_gather_fused():
