@@ -235,6 +235,14 @@ QEFT_API int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* sc
                     int dtype, unsigned flags, qeft_stream_t stream);
 
 /*
+ * Host-only: the launch plan qeft_gemm_w4_dx uses for [M, N, K] on a device with sm_count SMs (no GPU needed; tests and
+ * capacity planning).  *splits = CTAs that share a split tile (1: no tile is split), *whole_tiles = tiles computed by one
+ * CTA each (they come first in the grid), *ctas = the grid size.  Workspace of the launch: splits * M * K * 4 bytes when
+ * splits > 1.
+ */
+QEFT_API int qeft_gemm_w4_dx_plan(int M, int N, int K, int sm_count, int* splits, int* whole_tiles, int* ctas);
+
+/*
  * Gradient of the trainable outlier columns:  dow[N, r] (fp32) (+)= dy[M, N]^T . x[M, K-r:K].
  * accumulate != 0 adds into dow (gradient accumulation into the fp32 master grad).
  */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "qeft_gemm_w4": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_gemm_w4_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, C.POINTER(Gather), _vp]),
     "qeft_gemm_w4_dx": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
+    "qeft_gemm_w4_dx_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "qeft_dow": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "qeft_pack_w4": (_i, [_vp, _vp, _i, _i, _vp]),
     "qeft_unpack_w4": (_i, [_vp, _vp, _i, _i, _vp]),

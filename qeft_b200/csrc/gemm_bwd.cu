@@ -480,9 +480,50 @@ static int set_smem_once(Kern kern, size_t smem, bool (&done)[64]) {
   return QEFT_OK;
 }
 
+// Contraction split of a dX launch: cost in k-block times = sum over its waves of (k-blocks per CTA + the fixed cost of a
+// CTA); a split must win by 3 %.  Measured on B200: a k-block 0.75 us, an unsplit CTA ~1.5 us on top = 2 k-blocks, a
+// split CTA 17 us = 23 (the fp32 partial round trip).  Splitting every tile pays for launches of few tiles (M <= 512:
+// 1.4-2.5 x faster); at M = 2048 only the tiles of a nearly empty last wave are split (13B K = 5120: 160 tiles; 7B
+// K = 11008: 344).  force_all / force_tail > 1: every tile / the last wave's tiles that many ways (experiments).
+// Out: splits (CTAs per shared tile) and t_main (tiles computed whole, first in the grid).
+static void dx_plan(int tiles, int nkb, int nsm, size_t mk, int force_all, int force_tail, bool never, int* splits_out, int* t_main_out) {
+  int splits = 1, t_main = tiles;
+  const int sp_max = nkb / 12 < kDxMaxSplits ? nkb / 12 : kDxMaxSplits;     // (a split keeps at least 12 k-blocks)
+  const bool has_tail = tiles > nsm && tiles % nsm != 0;
+  if (force_tail > 1) {
+    if (has_tail && sp_max >= 2) { splits = force_tail < sp_max ? force_tail : sp_max; t_main = tiles - tiles % nsm; }
+  } else if (force_all > 1) {
+    if (sp_max >= 2) { splits = force_all < sp_max ? force_all : sp_max; t_main = 0; }
+  } else if (!never) {
+    long best = (long)cdiv(tiles, nsm) * (nkb + 2) * 100;
+    for (int sp = 2; sp <= sp_max; ++sp) {
+      const long part = cdiv(nkb, sp) + kDxSplitCost;
+      const long all = (long)cdiv(tiles * sp, nsm) * part * 103;
+      if (all < best) { best = all * 100 / 103; splits = sp; t_main = 0; }
+      if (has_tail) {
+        const long tail = ((long)(tiles / nsm) * (nkb + 2) + (long)cdiv((tiles % nsm) * sp, nsm) * part) * 103;
+        if (tail < best) { best = tail * 100 / 103; splits = sp; t_main = tiles - tiles % nsm; }
+      }
+    }
+  }
+  // (one arrival counter per tile; at most 1 GB of fp32 partials)
+  if (tiles > kSplitCounters || (size_t)splits * mk * sizeof(float) > ((size_t)1 << 30)) { splits = 1; t_main = tiles; }
+  *splits_out = splits;
+  *t_main_out = t_main;
+}
+
 }  // namespace qeft
 
 using namespace qeft;
+
+extern "C" int qeft_gemm_w4_dx_plan(int M, int N, int K, int sm_count, int* splits, int* whole_tiles, int* ctas) {
+  if (!splits || !whole_tiles || !ctas) return QEFT_E_NULL;
+  if (M <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 64 != 0 || sm_count <= 0) return QEFT_E_SHAPE;
+  const int tiles = cdiv(M, 256) * cdiv(K, kDxBF);
+  dx_plan(tiles, N / kDxBK, sm_count, (size_t)M * (size_t)K, 0, 0, false, splits, whole_tiles);
+  *ctas = *whole_tiles + (tiles - *whole_tiles) * *splits;
+  return QEFT_OK;
+}
 
 extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* scales, const void* scaled_zeros,
                                const void* oweight, void* dx, int M, int N, int K, int r, int G, int dtype,
@@ -518,11 +559,7 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
     static const int tbc_env = getenv("QEFT_DX_TBC") ? atoi(getenv("QEFT_DX_TBC")) : 0;
     prm.tbc = tbc_env == 1 ? 1 : 2;
   }
-  // Contraction split: cost of a launch in k-block times = sum over its waves of (k-blocks per CTA + the fixed cost of a
-  // CTA); a split must win by 3 %.  Measured on B200: a k-block 0.75 us, an unsplit CTA ~1.5 us on top = 2 k-blocks, a
-  // split CTA 17 us = 23 (the fp32 partial round trip).  Splitting every tile pays for launches of few tiles (M <= 512:
-  // 1.4-2.5 x faster); at M = 2048 only the tiles of a nearly empty last wave are split (13B K = 5120: 160 tiles; 7B
-  // K = 11008: 344).  QEFT_DX_SPLITS=1: never, =n: every tile n ways; QEFT_DX_TAIL=n: the last wave n ways.
+  // contraction split (dx_plan above).  QEFT_DX_SPLITS=1: never, =n: every tile n ways; QEFT_DX_TAIL=n: the last wave n ways
   const int ttok = cdiv(M, 128 * prm.tbc), tiles = ttok * cdiv(K, kDxBF);
   int splits = 1, t_main = tiles;
   prm.ws = nullptr; prm.counters = nullptr;
@@ -532,25 +569,7 @@ extern "C" int qeft_gemm_w4_dx(const void* dy, const void* qweight, const void* 
     int dev = 0, nsm = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
-    const int nkb = N / kDxBK;
-    const int sp_max = nkb / 12 < kDxMaxSplits ? nkb / 12 : kDxMaxSplits;     // (a split keeps at least 12 k-blocks)
-    if (tail_env > 1) {
-      if (tiles > nsm && tiles % nsm != 0 && sp_max >= 2) { splits = tail_env < sp_max ? tail_env : sp_max; t_main = tiles - tiles % nsm; }
-    } else if (split_env > 1) {
-      if (sp_max >= 2) { splits = split_env < sp_max ? split_env : sp_max; t_main = 0; }
-    } else if (split_env == 0) {
-      long best = (long)cdiv(tiles, nsm) * (nkb + 2) * 100;
-      for (int sp = 2; sp <= sp_max; ++sp) {
-        const long part = cdiv(nkb, sp) + kDxSplitCost;
-        const long all = (long)cdiv(tiles * sp, nsm) * part * 103;
-        if (all < best) { best = all * 100 / 103; splits = sp; t_main = 0; }
-        if (tiles > nsm && tiles % nsm != 0) {
-          const long tail = ((long)(tiles / nsm) * (nkb + 2) + (long)cdiv((tiles % nsm) * sp, nsm) * part) * 103;
-          if (tail < best) { best = tail * 100 / 103; splits = sp; t_main = tiles - tiles % nsm; }
-        }
-      }
-    }
-    if (tiles > kSplitCounters || (size_t)splits * (size_t)M * (size_t)K * sizeof(float) > ((size_t)1 << 30)) { splits = 1; t_main = tiles; }
+    dx_plan(tiles, N / kDxBK, nsm, (size_t)M * (size_t)K, split_env, tail_env, split_env == 1, &splits, &t_main);
     if (splits > 1) {
       st = split_workspace(static_cast<cudaStream_t>(stream), (size_t)splits * (size_t)M * (size_t)K * sizeof(float), &prm.ws, &prm.counters);
       if (st != QEFT_OK) return st;

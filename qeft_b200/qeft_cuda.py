@@ -244,6 +244,16 @@ def gemm_w4_dx(dy, qweight, scales, scaled_zeros, oweight, K, *, group_size=128,
     return out
 
 
+def gemm_w4_dx_plan(M: int, N: int, K: int, sm_count: int = 148):
+    """Host-only: ``(splits, whole_tiles, ctas)`` of the dX launch for this shape (see ``qeft_gemm_w4_dx_plan``)."""
+    import ctypes
+    sp, wt, ct = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    st = _lib.load().qeft_gemm_w4_dx_plan(int(M), int(N), int(K), int(sm_count), ctypes.byref(sp), ctypes.byref(wt),
+                                          ctypes.byref(ct))
+    _lib.check(st, "qeft_gemm_w4_dx_plan")
+    return sp.value, wt.value, ct.value
+
+
 def dow(dy, x, r, *, out=None, accumulate=False, pdl=None):
     """``dow[N, r] (fp32) (+)= dy^T . x[:, K-r:]``."""
     _need_cuda(dy, x)

@@ -184,3 +184,44 @@ def test_checkpoint_roundtrip_schema(tmp_path):
     missing, unexpected = m2.load_state_dict(ck["model_state_dict"], strict=False)
     assert not missing and not unexpected
     assert torch.equal(m2.q_proj.qweight, m.q_proj.qweight)
+
+
+def test_dx_launch_plan_host_logic():
+    """The dX launcher's contraction-split plan (host arithmetic, no GPU): which tiles are computed by one CTA and which
+    are shared by 2-4 CTAs.  The expected picks are the ones measured fastest on B200 (profiles/r02_dx_tail_split.log,
+    r02_dx_small_m_splits.log)."""
+    from qeft_b200 import qeft_cuda
+    plan = qeft_cuda.gemm_w4_dx_plan
+    # Llama-2-7B at M = 2048: one wave of 128 tiles -> no split; down_proj (K = 11008): 344 tiles = 2 waves + 48 tiles x 3
+    assert plan(2048, 4096, 4096) == (1, 128, 128)
+    assert plan(2048, 11008, 4096) == (1, 128, 128)
+    assert plan(2048, 4096, 11008) == (3, 296, 296 + 48 * 3)
+    # Llama-2-13B (BASELINE.json configs[3]): K = 5120 is 160 tiles = 148 whole + 12 x 4; K = 13824 (432 tiles) is not split
+    assert plan(2048, 5120, 5120) == (4, 148, 148 + 12 * 4)
+    assert plan(2048, 13824, 5120) == (4, 148, 148 + 12 * 4)
+    assert plan(2048, 5120, 13824) == (1, 432, 432)
+    # launches of few tiles: every tile split
+    assert plan(512, 4096, 4096) == (4, 0, 32 * 4)
+    assert plan(128, 11008, 4096) == (4, 0, 16 * 4)
+    assert plan(512, 4096, 11008) == (1, 86, 86)
+    # the fp32 partials of a launch stay under 1 GB
+    assert plan(16384, 13824, 5120)[0] * 16384 * 5120 * 4 <= 1 << 30
+    # a split keeps at least 12 k-blocks (N >= 1536 for two splits)
+    assert plan(256, 1024, 512)[0] == 1
+    # invariants over a sweep: the grid covers every tile, a shared tile has 2-4 CTAs, whole tiles fill whole waves
+    for M in (8, 100, 256, 640, 2048, 4096, 8192):
+        for N in (128, 1536, 4096, 5120, 11008, 13824):
+            for K in (256, 4096, 5120, 11008, 13824):
+                for sms in (148, 132, 64):
+                    sp, whole, ctas = plan(M, N, K, sms)
+                    tiles = -(-M // 256) * -(-K // 256)
+                    assert 1 <= sp <= 4 and 0 <= whole <= tiles and ctas == whole + (tiles - whole) * sp
+                    if sp == 1:
+                        assert whole == tiles
+                    else:
+                        assert (N // 64) // sp >= 12 and (whole == 0 or (whole % sms == 0 and whole < tiles))
+    lib = _lib.load()
+    import ctypes
+    z = ctypes.c_int(0)
+    assert lib.qeft_gemm_w4_dx_plan(2048, 4096, 4096, 148, None, ctypes.byref(z), ctypes.byref(z)) == -1
+    assert lib.qeft_gemm_w4_dx_plan(2048, 4000, 4096, 148, ctypes.byref(z), ctypes.byref(z), ctypes.byref(z)) == -2
