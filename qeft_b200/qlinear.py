@@ -14,6 +14,8 @@ reference checkpoints load unchanged.  What differs is below the API:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -21,6 +23,20 @@ from . import _lib, qeft_cuda
 from .reorder import sparse_to_dense_ids
 
 __all__ = ["QuantLinear", "QuantMatMul", "QuantMatMulQEFT", "pack_intweight", "pack_oweight", "unpack_intweight"]
+
+
+def _nvtx_wrapped(fn, label):
+    """``QEFT_NVTX=1``: an NVTX range around every forward, named after the dispatch target and the layer (the ranges
+    the reference carries commented out at qlinear.py:270,276,301,312,329).  Off by default: ``forward`` stays the bound
+    method itself."""
+    def forward(x):
+        torch.cuda.nvtx.range_push(label)
+        try:
+            return fn(x)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    forward.__name__ = fn.__name__
+    return forward
 
 
 # --------------------------------------------------------------------------------------------------
@@ -254,6 +270,8 @@ class QuantLinear(nn.Module):
             self.forward = self.forward_normal
             if training:
                 self.matmul = QuantMatMul.apply
+        if os.environ.get("QEFT_NVTX", "0") == "1":
+            self.forward = _nvtx_wrapped(self.forward, f"QuantLinear.{self.forward.__name__}:{self.name}")
 
     def set_for_wct(self):
         """Freeze the packed weight, make the outlier columns an fp32 trainable parameter (qlinear.py:239-242)."""

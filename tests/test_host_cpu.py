@@ -225,3 +225,32 @@ def test_dx_launch_plan_host_logic():
     z = ctypes.c_int(0)
     assert lib.qeft_gemm_w4_dx_plan(2048, 4096, 4096, 148, None, ctypes.byref(z), ctypes.byref(z)) == -1
     assert lib.qeft_gemm_w4_dx_plan(2048, 4000, 4096, 148, ctypes.byref(z), ctypes.byref(z), ctypes.byref(z)) == -2
+
+
+def test_nvtx_ranges_are_env_gated(monkeypatch):
+    """QEFT_NVTX=1 wraps the dispatch target chosen by set_kernel in an NVTX range; by default forward is
+    the bound method itself.  The wrapper keeps the name, passes errors through and closes its range."""
+    import torch
+    from qeft_b200.qlinear import QuantLinear
+
+    def make():
+        layer = QuantLinear(4, 256, 128, False, torch.float16, 64, 128, True, "model.layers.0.self_attn.o_proj")
+        layer.outlieridx = torch.arange(64)
+        layer.set_kernel(False)
+        return layer
+
+    monkeypatch.delenv("QEFT_NVTX", raising=False)
+    plain = make()
+    assert plain.forward == plain.forward_outlier_out_proj
+    monkeypatch.setenv("QEFT_NVTX", "1")
+    traced = make()
+    assert traced.forward != traced.forward_outlier_out_proj and traced.forward.__name__ == "forward_outlier_out_proj"
+    pushed, popped = [], []
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda s: pushed.append(s))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: popped.append(1))
+    try:
+        traced(torch.zeros(1, 256, dtype=torch.float16))      # no CPU path: raises inside the range
+        raise AssertionError("expected the CUDA-only error")
+    except RuntimeError as e:
+        assert "no CPU path" in str(e)
+    assert pushed == ["QuantLinear.forward_outlier_out_proj:model.layers.0.self_attn.o_proj"] and popped == [1]
