@@ -254,3 +254,38 @@ def test_nvtx_ranges_are_env_gated(monkeypatch):
     except RuntimeError as e:
         assert "no CPU path" in str(e)
     assert pushed == ["QuantLinear.forward_outlier_out_proj:model.layers.0.self_attn.o_proj"] and popped == [1]
+
+
+def test_packers_property_random_shapes():
+    """Property test over random legal shapes (hypothesis): the product's closed-form host packers agree bit for bit with
+    the oracle's restatement of qlinear.py:70-121 (itself pinned to reference outputs above), unpack inverts pack, and a
+    one-nibble change moves exactly one nibble of the packed image (the layout is a permutation of nibbles)."""
+    from hypothesis import given, settings, strategies as st
+    import oracle
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 4), st.integers(1, 5), st.integers(0, 2 ** 31 - 1))
+    def check(n8, k64, seed):
+        N, K = 8 * n8, 64 * k64                      # (pack_oweight interleaves blocks of 8 rows)
+        rng = np.random.default_rng(seed)
+        q = rng.integers(0, 16, size=(N, K), dtype=np.int32)
+        packed = pack_intweight(torch.tensor(q), interleave=4, kstride=64)
+        assert packed.shape == (N // 4, K) and packed.dtype == torch.int16
+        assert np.array_equal(packed.numpy(), oracle.pack_intweight(q))
+        assert np.array_equal(unpack_intweight(packed).numpy(), q)
+        assert np.array_equal(oracle.unpack_intweight(packed.numpy()), q)
+        # flip one weight: exactly one nibble of one int16 changes
+        i, j = int(rng.integers(0, N)), int(rng.integers(0, K))
+        q2 = q.copy()
+        q2[i, j] ^= 0xF
+        diff = packed.numpy().view(np.uint16) ^ pack_intweight(torch.tensor(q2), 4, 64).numpy().view(np.uint16)
+        nz = diff[diff != 0]
+        assert nz.size == 1 and int(nz[0]) in (0xF, 0xF0, 0xF00, 0xF000)
+        # outlier columns: interleave is a permutation of fp16 values, inverted by the oracle's unpacker
+        r = 32 * int(rng.integers(1, 5))
+        ow = rng.standard_normal((N, r)).astype(np.float16)
+        owi = pack_oweight(torch.tensor(ow), interleave=4)
+        assert np.array_equal(owi.numpy().view(np.uint16), oracle.pack_oweight(ow).view(np.uint16))
+        assert np.array_equal(oracle.unpack_oweight(owi.numpy()).view(np.uint16), ow.view(np.uint16))
+
+    check()
