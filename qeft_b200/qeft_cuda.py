@@ -168,6 +168,9 @@ def _check_packed(what, x_dtype, qweight, scales, scaled_zeros, oweight, bias, K
     have the shape the kernel will index with ``group_size``, be fp16 like the checkpoint, and the dense outlier block
     must have the activations' dtype (the kernels copy its bits unconverted)."""
     N = qweight.shape[0] * 4
+    if qweight.dim() != 2 or qweight.shape[1] != K or qweight.dtype != torch.int16 or not qweight.is_contiguous():
+        raise RuntimeError(f"{what}: qweight must be a contiguous int16 [N / 4, {K}] tensor (pack_intweight), found "
+                           f"{qweight.dtype} {tuple(qweight.shape)}")
     G = K if group_size in (-1, K) else group_size
     if G <= 0 or K % G != 0:
         raise RuntimeError(f"{what}: group_size {group_size} does not divide K = {K}")
@@ -184,6 +187,13 @@ def _check_packed(what, x_dtype, qweight, scales, scaled_zeros, oweight, bias, K
                            "cast the outlier columns to the activations' dtype")
 
 
+def _check_out(what, out, shape_numel, dtype, device):
+    """A caller-provided result tensor is written through its raw pointer: it must be exactly what the kernel assumes."""
+    if out.dtype != dtype or out.numel() != shape_numel or not out.is_contiguous() or out.device != device:
+        raise RuntimeError(f"{what}: out must be a contiguous {dtype} tensor of {shape_numel} elements on {device}, found "
+                           f"{out.dtype} {tuple(out.shape)} on {out.device}")
+
+
 def gemm_w4(x, qweight, scales, scaled_zeros, oweight, bias, *, group_size=128, out=None, pdl=None):
     """``y = x . Wdense^T (+ bias)``; ``oweight`` plain ``[N, r]`` fp16/bf16 or None (r = 0)."""
     _need_cuda(x, qweight, scales, scaled_zeros, oweight, bias)
@@ -198,6 +208,8 @@ def gemm_w4(x, qweight, scales, scaled_zeros, oweight, bias, *, group_size=128, 
         oweight = oweight.contiguous()
     if out is None:
         out = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+    else:
+        _check_out("gemm_w4", out, M * N, x.dtype, x.device)
     with _on(x):
         st = _lib.load().qeft_gemm_w4(_ptr(x), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
                                       _ptr(bias), _ptr(out), M, N, K, r, group_size, dt, _flags(pdl), _stream(x))
@@ -235,8 +247,12 @@ def gemm_w4_dx(dy, qweight, scales, scaled_zeros, oweight, K, *, group_size=128,
     if qweight.shape[0] * 4 != N:
         raise RuntimeError(f"gemm_w4_dx: dy has {N} features but qweight packs {qweight.shape[0] * 4} rows")
     _check_packed("gemm_w4_dx", dy.dtype, qweight, scales, scaled_zeros, oweight, None, K, group_size)
+    if oweight is not None and not oweight.is_contiguous():
+        oweight = oweight.contiguous()               # (the kernel's TMA map assumes rows of r elements)
     if out is None:
         out = torch.empty(dy.shape[:-1] + (K,), dtype=dy.dtype, device=dy.device)
+    else:
+        _check_out("gemm_w4_dx", out, M * K, dy.dtype, dy.device)
     with _on(dy):
         st = _lib.load().qeft_gemm_w4_dx(_ptr(dy), _ptr(qweight), _ptr(scales), _ptr(scaled_zeros), _ptr(oweight),
                                          _ptr(out), M, N, K, r, group_size, dt, _flags(pdl), _stream(dy))

@@ -289,3 +289,36 @@ def test_packers_property_random_shapes():
         assert np.array_equal(oracle.unpack_oweight(owi.numpy()).view(np.uint16), ow.view(np.uint16))
 
     check()
+
+
+def test_wrapper_validation_of_packed_operands():
+    """What the C ABI cannot see (pointers only) is checked by the Python wrappers before a launch: qweight is the packed
+    int16 [N / 4, K] image of THIS K, the scale tables have the shape the kernel indexes with group_size, dtypes are the
+    checkpoint's, a caller-provided result tensor is exactly what the kernel writes."""
+    import pytest
+    import oracle
+    from qeft_b200 import qeft_cuda
+    N, K, r, G = 128, 256, 64, 128
+    L = oracle.synth_layer(N, K, r=r, G=G, seed=1, bias=True)
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(a))  # noqa: E731
+    qw, sc, sz, ow, b = d(L["qweight"]), d(L["scales"]), d(L["scaled_zeros"]), d(L["oweight"]), d(L["bias"])
+    chk = qeft_cuda._check_packed
+    chk("t", torch.float16, qw, sc, sz, ow, b, K, G)                       # the shapes every call site passes
+    chk("t", torch.float16, qw[: N // 8], sc[:, : N // 2].contiguous(), sz[:, : N // 2].contiguous(), ow[: N // 2], None, K, G)   # a row shard
+    with pytest.raises(RuntimeError, match="qweight"):
+        chk("t", torch.float16, qw, sc, sz, ow, b, K // 2, G)              # activations of another width
+    with pytest.raises(RuntimeError, match="qweight"):
+        chk("t", torch.float16, qw.to(torch.int32), sc, sz, ow, b, K, G)
+    with pytest.raises(RuntimeError, match="qweight"):
+        chk("t", torch.float16, qw[:, ::2][:, : K // 2], sc, sz, ow, b, K // 2, G)   # non-contiguous view
+    with pytest.raises(RuntimeError, match="scales"):
+        chk("t", torch.float16, qw, sc, sz, ow, b, K, 64)                  # packed with another group size
+    with pytest.raises(RuntimeError, match="Half"):
+        chk("t", torch.float16, qw, sc.float(), sz, ow, b, K, G)
+    with pytest.raises(RuntimeError, match="oweight"):
+        chk("t", torch.bfloat16, qw, sc, sz, ow, b, K, G)                  # fp16 outlier block under bf16 activations
+    out = torch.empty((8, N), dtype=torch.float16)
+    qeft_cuda._check_out("t", out, 8 * N, torch.float16, out.device)
+    for bad in (out.float(), out[:, : N // 2], torch.empty((4, N), dtype=torch.float16)):
+        with pytest.raises(RuntimeError, match="out must be"):
+            qeft_cuda._check_out("t", bad, 8 * N, torch.float16, out.device)
